@@ -1,0 +1,100 @@
+"""Shared test helpers: rebuild duck-typed model / prior objects from the specs stored in tests/golden."""
+import json
+import types
+
+import numpy as np
+
+
+def prior_from_dict(d):
+    """Namespace object carrying the reference's attribute names; class name preserved for the oracle."""
+    obj = type(d["cls"], (), {})()
+    obj._mro_names = list(d.get("mro", []))     # the oracle converter resolves subclasses through these
+    obj._bounds = None if d["_bounds"] is None else tuple(d["_bounds"])
+    obj._norm = d["_norm"]
+    for k in ("alpha", "mean", "sigma", "norm", "lognorm", "mu", "scale", "log_s", "halo_fraction", "local"):
+        if k in d:
+            setattr(obj, k, d[k])
+    if "components" in d:
+        obj.components = [prior_from_dict(c) for c in d["components"]]
+        obj.n_components = d["n_components"]
+        obj.breakpoints = d["breakpoints"]
+        obj.norms = np.array(d["norms"])
+        obj.lognorms = np.array(d["lognorms"])
+    if "orig_prior" in d:
+        obj.orig_prior = prior_from_dict(d["orig_prior"])
+        obj.orig_par = d["orig_par"]
+        obj.deriv_prop = d["deriv_prop"]
+    return obj
+
+
+class ArrayInterp:
+    def __init__(self, grid, axes, columns):
+        self.grid = np.ascontiguousarray(grid, dtype=float)
+        self.index_columns = tuple(np.asarray(a, dtype=float) for a in axes)
+        self.columns = [str(c) for c in columns]
+        self.column_index = {c: i for i, c in enumerate(self.columns)}
+        self.ndim = len(self.index_columns)
+        self.n_columns = len(self.columns)
+
+
+def golden_grids(gi):
+    """(track, iso, bc) dicts as produced by isochrones_b200.synthetic from the golden interp file."""
+    out = {}
+    for prefix, nd in (("trk", 3), ("iso", 3), ("bc", 4)):
+        out[prefix] = {
+            "grid": gi[prefix + "_grid"],
+            "axes": tuple(gi["%s_ax%d" % (prefix, i)] for i in range(nd)),
+            "columns": [str(c) for c in gi[prefix + "_columns"]],
+        }
+    return out["trk"], out["iso"], out["bc"]
+
+
+def ns_model_from_spec(spec, model, bc):
+    """Duck-typed BasicStarModel stand-in (attributes read by oracle.StarModel) from a golden spec."""
+    kind = spec["kind"]
+    ic = types.SimpleNamespace(
+        param_index_order=[2, 0, 1, 3, 4] if kind == "track" else [1, 2, 0, 3, 4],
+        eep_replaces="age" if kind == "track" else "mass",
+        model_grid=types.SimpleNamespace(interp=ArrayInterp(model["grid"], model["axes"], model["columns"])),
+        bc_grid=types.SimpleNamespace(interp=ArrayInterp(bc["grid"], bc["axes"], bc["columns"]), bands=bc["columns"]),
+    )
+    kwargs = {k: (np.float64(v[0]), np.float64(v[1])) for k, v in spec["kwargs"].items()}
+    mod = types.SimpleNamespace(
+        ic=ic, N=spec["N"], kwargs=kwargs, bands=list(spec["bands"]),
+        spec_props=[kwargs.get(k, (np.nan, np.nan)) for k in ["Teff", "logg", "feh"]],
+        _priors={k: prior_from_dict(v) for k, v in spec["priors"].items()},
+        param_names=tuple(spec["param_names"]),
+    )
+    return mod
+
+
+def load_specs(gl):
+    return json.loads(str(gl["lp_specs_json"]))
+
+
+def assert_same_special(a, b):
+    """NaN / +-inf patterns must be identical."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    assert np.array_equal(np.isposinf(a), np.isposinf(b)), "+inf pattern differs"
+    assert np.array_equal(np.isneginf(a), np.isneginf(b)), "-inf pattern differs"
+
+
+def max_rel_err(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    m = np.isfinite(a) & np.isfinite(b)
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-300)))
+
+
+def max_abs_err(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    m = np.isfinite(a) & np.isfinite(b)
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(a[m] - b[m])))
