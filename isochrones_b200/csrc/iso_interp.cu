@@ -1,0 +1,255 @@
+// isochrones_b200 — batched multilinear interpolation kernels.
+//
+//   iso_interp_values  replaces interp_values_2d/3d/4d (interp.py:341-392), i.e. the serial loop over
+//                      interp_value_* (:208-338), find_indices_* (:63-205) and searchsorted (:10-35);
+//   iso_interp_mags    replaces interp_mags (mags.py:64-124) over interp_mag (mags.py:8-61).
+//
+// One thread per point.  The 2^ndim corner offsets and weights are computed once per point and kept in
+// registers; columns are the outer loop, corners the inner one, so each output accumulates in the reference's
+// corner order (zero-weight corners are read and multiplied: NaN * 0 = NaN must propagate, interp.py:286-291).
+#include "iso_common.cuh"
+
+#define ISO_INTERP_THREADS 256
+
+struct IsoInterpArgs {
+    const double *x[ISO_MAX_DIM];   // device coordinate arrays, each [N]
+    const int *icols;               // device [ncols]
+    double *out;                    // device [N, ncols]
+    long long N;
+    int ncols;
+};
+
+template <int NDIM>
+__global__ void __launch_bounds__(ISO_INTERP_THREADS)
+iso_interp_values_kernel(IsoGridDev g, IsoInterpArgs a)
+{
+    const double nan = iso_nan();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+        double x[NDIM], y[NDIM];
+        int idx[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) x[d] = a.x[d][i];
+        double *o = a.out + i * a.ncols;
+        if (!iso_locate<NDIM>(g, g.nodes, x, idx, y)) {
+            for (int c = 0; c < a.ncols; c++) o[c] = nan;
+            continue;
+        }
+        unsigned node[1 << NDIM];
+        double w[1 << NDIM];
+        iso_corners<NDIM>(g, idx, y, node, w);
+        for (int c = 0; c < a.ncols; c++) {
+            int ic = __ldg(a.icols + c);
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < (1 << NDIM); j++) acc = fma(__ldg(g.g + (size_t)node[j] * g.ncols + ic), w[j], acc);
+            o[c] = acc;
+        }
+    }
+}
+
+struct IsoMagsArgs {
+    const double *pars[5];          // device, parameter-major: pars[j][i]  (mags.py:86-87)
+    int index_order[5];
+    int i_Teff, i_logg, i_feh, i_Mbol;
+    const int *bc_cols;             // device [n_bands]
+    int n_bands;
+    long long N;
+    double *Teff, *logg, *feh, *mags;   // device [N], [N], [N], [N, n_bands]
+};
+
+__global__ void __launch_bounds__(ISO_INTERP_THREADS)
+iso_interp_mags_kernel(IsoGridDev model, IsoGridDev bc, IsoMagsArgs a)
+{
+    const double nan = iso_nan();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+        double p[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) p[j] = a.pars[j][i];
+        double q[5];   // q[d] = pars[index_order[d]]
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            int io = a.index_order[d];
+            q[d] = io == 0 ? p[0] : io == 1 ? p[1] : io == 2 ? p[2] : io == 3 ? p[3] : p[4];
+        }
+        // star_props = interp_value_3d(..., [i_Teff, i_logg, i_feh, i_Mbol])   mags.py:35-47
+        double props[4] = {nan, nan, nan, nan};
+        {
+            double x[3] = {q[0], q[1], q[2]}, y[3];
+            int idx[3];
+            if (iso_locate<3>(model, model.nodes, x, idx, y)) {
+                unsigned node[8];
+                double w[8];
+                iso_corners<3>(model, idx, y, node, w);
+                const int cols[4] = {a.i_Teff, a.i_logg, a.i_feh, a.i_Mbol};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc = fma(__ldg(model.g + (size_t)node[j] * model.ncols + cols[c]), w[j], acc);
+                    props[c] = acc;
+                }
+            }
+        }
+        a.Teff[i] = props[0];
+        a.logg[i] = props[1];
+        a.feh[i] = props[2];
+        // bc = interp_value_4d(Teff, logg, feh, AV, ...)   mags.py:49-50 — the BC lookup uses the interpolated
+        // surface feh; mags = Mbol + 5 log10(d / 10) - bc   mags.py:52-59
+        double dist_mod = 5.0 * log10(q[3] / 10.0);
+        double *m = a.mags + i * a.n_bands;
+        double x4[4] = {props[0], props[1], props[2], q[4]}, y4[4];
+        int idx4[4];
+        if (!iso_locate<4>(bc, bc.nodes, x4, idx4, y4)) {
+            for (int b = 0; b < a.n_bands; b++) m[b] = nan;
+            continue;
+        }
+        unsigned node[16];
+        double w[16];
+        iso_corners<4>(bc, idx4, y4, node, w);
+        for (int b = 0; b < a.n_bands; b++) {
+            int ic = __ldg(a.bc_cols + b);
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc = fma(__ldg(bc.g + (size_t)node[j] * bc.ncols + ic), w[j], acc);
+            m[b] = props[3] + dist_mod - acc;
+        }
+    }
+}
+
+static int grid_blocks(iso_ctx *ctx, int64_t n, int threads)
+{
+    int64_t want = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 16;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+struct InterpUser {
+    const iso_grid *grid;
+    const int *d_icols;
+    int ncols;
+};
+
+static int interp_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    (void)row0;
+    InterpUser *u = (InterpUser *)user;
+    IsoInterpArgs a;
+    int ndim = u->grid->dev.ndim;
+    for (int k = 0; k < ISO_MAX_DIM; k++) a.x[k] = k < ndim ? (const double *)d[k] : nullptr;
+    a.icols = u->d_icols;
+    a.out = (double *)d[ndim];
+    a.N = n;
+    a.ncols = u->ncols;
+    int blocks = grid_blocks(ctx, n, ISO_INTERP_THREADS);
+    if (ndim == 2) iso_interp_values_kernel<2><<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->grid->dev, a);
+    else if (ndim == 3) iso_interp_values_kernel<3><<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->grid->dev, a);
+    else iso_interp_values_kernel<4><<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->grid->dev, a);
+    ctx->launches++;
+    ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+struct MagsUser {
+    const iso_grid *model, *bc;
+    IsoMagsArgs proto;
+};
+
+static int mags_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    (void)row0;
+    MagsUser *u = (MagsUser *)user;
+    IsoMagsArgs a = u->proto;
+    for (int j = 0; j < 5; j++) a.pars[j] = (const double *)d[j];
+    a.Teff = (double *)d[5];
+    a.logg = (double *)d[6];
+    a.feh = (double *)d[7];
+    a.mags = (double *)d[8];
+    a.N = n;
+    int blocks = grid_blocks(ctx, n, ISO_INTERP_THREADS);
+    iso_interp_mags_kernel<<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->model->dev, u->bc->dev, a);
+    ctx->launches++;
+    ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+// small device array of ints that lives for the duration of one host call
+struct DevInts {
+    int *d = nullptr;
+    ~DevInts() { if (d) cudaFree(d); }
+    int upload(iso_ctx *ctx, const int32_t *h, int n)
+    {
+        ISO_CUDA(ctx, cudaMalloc(&d, sizeof(int) * (n > 0 ? n : 1)));
+        if (n > 0) ISO_CUDA(ctx, cudaMemcpy(d, h, sizeof(int) * n, cudaMemcpyHostToDevice));
+        return ISO_OK;
+    }
+};
+
+extern "C" {
+
+int iso_interp_values(iso_ctx *ctx, const iso_grid *grid, const double *const *h_x, int64_t N, const int32_t *icols,
+                      int ncols, double *h_out)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_values: ctx is NULL");
+    ISO_REQUIRE(ctx, grid && h_x && icols, "iso_interp_values: NULL argument");
+    ISO_REQUIRE(ctx, grid->device == ctx->device, "iso_interp_values: grid belongs to another device");
+    ISO_REQUIRE(ctx, N >= 0 && ncols >= 1, "iso_interp_values: bad sizes");
+    ISO_REQUIRE(ctx, N == 0 || h_out, "iso_interp_values: out is NULL");
+    for (int c = 0; c < ncols; c++)
+        ISO_REQUIRE(ctx, icols[c] >= 0 && icols[c] < grid->dev.ncols, "iso_interp_values: column index out of range");
+    int ndim = grid->dev.ndim;
+    for (int d = 0; d < ndim; d++) ISO_REQUIRE(ctx, N == 0 || h_x[d], "iso_interp_values: NULL coordinate array");
+    if (N == 0) return ISO_OK;
+    IsoDeviceGuard guard(ctx->device);
+    DevInts cols;
+    int rc = cols.upload(ctx, icols, ncols);
+    if (rc != ISO_OK) return rc;
+    IsoPipeArray arr[ISO_MAX_DIM + 1];
+    for (int d = 0; d < ndim; d++) arr[d] = IsoPipeArray{h_x[d], nullptr, 8};
+    arr[ndim] = IsoPipeArray{nullptr, h_out, (int64_t)8 * ncols};
+    InterpUser u{grid, cols.d, ncols};
+    return iso_run_pipeline(ctx, N, arr, ndim + 1, interp_launch, &u);
+}
+
+int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5], int i_Teff,
+                    int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands, const double *h_pars,
+                    int64_t N, double *h_Teff, double *h_logg, double *h_feh, double *h_mags)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_mags: ctx is NULL");
+    ISO_REQUIRE(ctx, model && bc && index_order, "iso_interp_mags: NULL argument");
+    ISO_REQUIRE(ctx, model->device == ctx->device && bc->device == ctx->device, "iso_interp_mags: grid on another device");
+    ISO_REQUIRE(ctx, model->dev.ndim == 3 && bc->dev.ndim == 4, "iso_interp_mags: model grid must be 3-D, BC grid 4-D");
+    ISO_REQUIRE(ctx, N >= 0 && n_bands >= 0, "iso_interp_mags: bad sizes");
+    ISO_REQUIRE(ctx, n_bands == 0 || bc_cols, "iso_interp_mags: bc_cols is NULL");
+    int mc = model->dev.ncols;
+    ISO_REQUIRE(ctx, i_Teff >= 0 && i_Teff < mc && i_logg >= 0 && i_logg < mc && i_feh >= 0 && i_feh < mc && i_Mbol >= 0 &&
+                         i_Mbol < mc, "iso_interp_mags: model column index out of range");
+    for (int b = 0; b < n_bands; b++)
+        ISO_REQUIRE(ctx, bc_cols[b] >= 0 && bc_cols[b] < bc->dev.ncols, "iso_interp_mags: band column out of range");
+    for (int j = 0; j < 5; j++)
+        ISO_REQUIRE(ctx, index_order[j] >= 0 && index_order[j] < 5, "iso_interp_mags: bad index_order");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_pars && h_Teff && h_logg && h_feh && (n_bands == 0 || h_mags), "iso_interp_mags: NULL buffer");
+    IsoDeviceGuard guard(ctx->device);
+    DevInts cols;
+    int rc = cols.upload(ctx, bc_cols, n_bands);
+    if (rc != ISO_OK) return rc;
+    IsoPipeArray arr[9];
+    for (int j = 0; j < 5; j++) arr[j] = IsoPipeArray{h_pars + (size_t)j * N, nullptr, 8};
+    arr[5] = IsoPipeArray{nullptr, h_Teff, 8};
+    arr[6] = IsoPipeArray{nullptr, h_logg, 8};
+    arr[7] = IsoPipeArray{nullptr, h_feh, 8};
+    arr[8] = IsoPipeArray{nullptr, n_bands ? h_mags : nullptr, (int64_t)8 * (n_bands > 0 ? n_bands : 1)};
+    MagsUser u;
+    u.model = model;
+    u.bc = bc;
+    for (int j = 0; j < 5; j++) u.proto.index_order[j] = index_order[j];
+    u.proto.i_Teff = i_Teff;
+    u.proto.i_logg = i_logg;
+    u.proto.i_feh = i_feh;
+    u.proto.i_Mbol = i_Mbol;
+    u.proto.bc_cols = cols.d;
+    u.proto.n_bands = n_bands;
+    return iso_run_pipeline(ctx, N, arr, 9, mags_launch, &u);
+}
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// isochrones_b200 — fused lnprior + lnlike + lnpost kernel.
+//
+// One launch turns rows of parameter vectors into log-posterior values.  It replaces, per row, the chain
+//   StarModel.lnpost            starmodel.py:538-542
+//   BasicStarModel.lnprior      starmodel.py:1616-1635   (+ the prior classes, iso_prior.cuh; EEP_prior priors.py:409-429)
+//   BasicStarModel.lnlike       starmodel.py:1563-1614
+//   star_lnlike                 likelihood.py:16-147     (gauss_lnprob :10-13, fast_addmags utils.py:67-75)
+//   interp_mag                  mags.py:8-61             (interp_value_3d / _4d interp.py:252-338)
+//
+// Data movement per row and star: the model-grid cell is gathered ONCE — 8 corners x one 64-byte
+// node of the 8-column model pack (Teff, logg, feh, Mbol for interp_mag; age|mass and dt_deep|dm_deep for the
+// EEP prior; nu_max, delta_nu) as 2 x LDG.256 per corner — and the BC cell as 16 corners x one 32-byte sector per
+// chunk of 4 packed bands.  The reference gathers the same model cell twice (once in EEP_prior, once in
+// interp_mag) and a third time for asteroseismology.
+#include "iso_common.cuh"
+#include "iso_prior.cuh"
+
+#define ISO_LNPOST_THREADS 256
+
+// device image of one star model (built from the public iso_model by iso_models_stage)
+struct IsoGaussDev {
+    double val;   // observed value
+    double c;     // log(1 / sqrt(2 pi)) + log(unc)      (likelihood.py:13 — note the PLUS sign)
+    double h;     // 1 / (unc * unc)
+};
+
+struct IsoModelDev {
+    int n_stars, eep_replaces_age;
+    int index_order[5];
+    int obs_mask;          // bit c: BC-pack column c is an observed band
+    int spec_mask;         // bit i: Teff / logg / feh observed (value not NaN, likelihood.py:127)
+    int has_plax, has_nu_max, has_delta_nu;
+    int eep_has_bounds;
+    int pad_;
+    IsoGaussDev spec[3];
+    IsoGaussDev mag[ISO_MAX_BANDS];   // indexed by BC-pack column
+    IsoGaussDev plax, nu_max, delta_nu;
+    double eep_lo, eep_hi, eep_norm;
+    iso_prior eep_orig, mass, age, feh, distance, AV;
+};
+
+struct iso_models {
+    IsoModelDev *d_models = nullptr;
+    int n_models = 0;
+    int n_stars = 0;
+    int device = 0;
+    int max_col = -1;      // highest BC-pack column any model observes
+    bool needs_seismo = false;
+};
+
+struct IsoLnpostArgs {
+    const IsoModelDev *models;
+    const int *model_of_row;   // catalog mode only
+    const double *pars;        // [N, 4 + n_stars] row-major
+    double *lnpost, *lnprior, *lnlike;   // [N]; lnprior / lnlike may be NULL
+    long long N;
+    int smem_axis_off[2][ISO_MAX_DIM];   // offset (in double2) of each axis table in shared memory; -1: closed form
+    int smem_nodes;                      // double2 entries of axis tables in shared memory
+};
+
+__device__ __forceinline__ double iso_gauss(const IsoGaussDev &g, double model_val)
+{
+    double resid = g.val - model_val;
+    return g.c - 0.5 * resid * resid * g.h;
+}
+
+__device__ __forceinline__ double iso_sel5(const double (&a)[5], int i)
+{
+    return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : i == 3 ? a[3] : a[4];
+}
+
+template <int NDIM>
+__device__ __forceinline__ bool iso_locate_smem(const IsoGridDev &g, const double2 *smem, const int (&soff)[ISO_MAX_DIM],
+                                                const double (&x)[NDIM], int (&idx)[NDIM], double (&y)[NDIM])
+{
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) ok = ok && iso_in_bounds(g.ax[d], x[d]);
+    if (!ok) return false;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) idx[d] = iso_axis_locate(g.ax[d], smem + soff[d], x[d], y[d]);
+    return true;
+}
+
+template <int NSTARS, bool CATALOG>
+__global__ void __launch_bounds__(ISO_LNPOST_THREADS)
+iso_lnpost_kernel(const IsoGridDev mg, const IsoGridDev bg, const IsoLnpostArgs a)
+{
+    constexpr int NDIMP = NSTARS + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
+    IsoModelDev *s_model = reinterpret_cast<IsoModelDev *>(smem_raw + sizeof(double2) * a.smem_nodes);
+
+    // stage the axis tables (and, outside catalog mode, the star model) in shared memory
+    for (int g = 0; g < 2; g++) {
+        const IsoGridDev &gr = g == 0 ? mg : bg;
+        for (int d = 0; d < gr.ndim; d++) {
+            int so = a.smem_axis_off[g][d];
+            if (so < 0) continue;
+            for (int t = threadIdx.x; t < gr.ax[d].n; t += blockDim.x) s_nodes[so + t] = gr.nodes[gr.ax[d].off + t];
+        }
+    }
+    if (!CATALOG) {
+        const int *src = reinterpret_cast<const int *>(a.models);
+        int *dst = reinterpret_cast<int *>(s_model);
+        for (int t = threadIdx.x; t < (int)(sizeof(IsoModelDev) / sizeof(int)); t += blockDim.x) dst[t] = src[t];
+    }
+    __syncthreads();
+
+    const double nan = iso_nan();
+    const double neg_inf = iso_neg_inf();
+    const bool want_parts = (a.lnprior != nullptr) || (a.lnlike != nullptr);
+    const int bc_chunks = bg.ncols >> 2;
+
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+        const IsoModelDev &m = CATALOG ? a.models[a.model_of_row[i]] : *s_model;
+        double p[NDIMP];
+#pragma unroll
+        for (int j = 0; j < NDIMP; j++) p[j] = a.pars[i * NDIMP + j];
+        const double other = p[NSTARS], feh_in = p[NSTARS + 1], dist = p[NSTARS + 2], AV = p[NSTARS + 3];
+
+        // ---- priors that need no grid access; order of the final sum follows param_names ----------------
+        bool order_bad = false;   // starmodel.py:1618-1623 (N = 3 precedence as written in the reference)
+        if (NSTARS == 2) order_bad = p[1] > p[0];
+        if (NSTARS == 3) order_bad = !(p[0] > p[1]) && (p[1] > p[2]);
+        // track grids (mass, eep, feh, ..): p[0] is the mass (prior "mass") and `other` the EEP;
+        // isochrone grids (eep_0.., age, feh, ..): p[k] are the EEPs and `other` the age (prior "age")
+        const double lnp_other = m.eep_replaces_age ? iso_prior_lnpdf(m.mass, p[0]) : iso_prior_lnpdf(m.age, other);
+        const double lnp_feh = iso_prior_lnpdf(m.feh, feh_in);
+        const double lnp_dist = iso_prior_lnpdf(m.distance, dist);
+        const double lnp_AV = iso_prior_lnpdf(m.AV, AV);
+        const double cheap = lnp_other + lnp_feh + lnp_dist + lnp_AV;
+        if (!want_parts && (order_bad || !isfinite(cheap))) {
+            // lnprior is already known to be -inf or NaN: StarModel.lnpost returns -inf (starmodel.py:540-541)
+            a.lnpost[i] = neg_inf;
+            continue;
+        }
+
+        // ---- model-grid gather per star --------------------------------------------------------------
+        double lnp_eep[NSTARS], Mbol[NSTARS], y4[NSTARS][4];
+        int idx4[NSTARS][4];
+        bool bc_ok[NSTARS];
+        double Teff = nan, logg = nan, feh_s = nan, nu_max = nan, delta_nu = nan;
+#pragma unroll
+        for (int k = 0; k < NSTARS; k++) {
+            // star k uses [pars[k], shared parameters...]  (likelihood.py:43-54)
+            const double sp[5] = {p[k], other, feh_in, dist, AV};
+            const double x[3] = {iso_sel5(sp, m.index_order[0]), iso_sel5(sp, m.index_order[1]), iso_sel5(sp, m.index_order[2])};
+            double y[3];
+            int idx[3];
+            double v[8] = {nan, nan, nan, nan, nan, nan, nan, nan};
+            if (iso_locate_smem<3>(mg, s_nodes, a.smem_axis_off[0], x, idx, y)) {
+                unsigned node[8];
+                double w[8];
+                iso_corners<3>(mg, idx, y, node, w);
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double *base = mg.g + (size_t)node[j] * ISO_MP_NCOLS;
+                    iso_d4 lo = iso_ldg256(base), hi = iso_ldg256(base + 4);
+                    v[0] = fma(lo.x, w[j], v[0]);
+                    v[1] = fma(lo.y, w[j], v[1]);
+                    v[2] = fma(lo.z, w[j], v[2]);
+                    v[3] = fma(lo.w, w[j], v[3]);
+                    v[4] = fma(hi.x, w[j], v[4]);
+                    v[5] = fma(hi.y, w[j], v[5]);
+                    v[6] = fma(hi.z, w[j], v[6]);
+                    v[7] = fma(hi.w, w[j], v[7]);
+                }
+            }
+            // EEP_prior.lnpdf: BoundedPrior.lnpdf :131-140 -> Prior.pdf :54-59 -> EEP_prior._pdf :423-429
+            const double eep = m.eep_replaces_age ? other : p[k];
+            if (m.eep_has_bounds && iso_outside(eep, m.eep_lo, m.eep_hi)) {
+                lnp_eep[k] = neg_inf;
+            } else {
+                double pdf = iso_prior_call(m.eep_orig, v[ISO_MP_ORIG]) * v[ISO_MP_DERIV];
+                lnp_eep[k] = iso_log_or_neginf(pdf / m.eep_norm);
+            }
+            Mbol[k] = v[ISO_MP_MBOL];
+            if (k == 0) {   // companions' Teff / logg / feh are discarded (likelihood.py:76, 96)
+                Teff = v[ISO_MP_TEFF];
+                logg = v[ISO_MP_LOGG];
+                feh_s = v[ISO_MP_FEH];
+                nu_max = v[ISO_MP_NU_MAX];
+                delta_nu = v[ISO_MP_DELTA_NU];
+            }
+            // BC cell of this star: interp_value_4d(Teff, logg, feh, AV)  mags.py:49-50
+            const double x4[4] = {v[ISO_MP_TEFF], v[ISO_MP_LOGG], v[ISO_MP_FEH], AV};
+            bc_ok[k] = iso_locate_smem<4>(bg, s_nodes, a.smem_axis_off[1], x4, idx4[k], y4[k]);
+        }
+
+        // ---- lnprior: sum in param_names order (models.py:665, 692; starmodel.py:1510-1518) ----------------
+        double lnprior;
+        if (order_bad) {
+            lnprior = neg_inf;
+        } else {
+            lnprior = 0.0;
+            if (m.eep_replaces_age) {   // (mass, eep, feh, distance, AV)
+                lnprior += lnp_other;
+                lnprior += lnp_eep[0];
+            } else {                    // (eep_0 .. eep_{N-1}, age, feh, distance, AV)
+#pragma unroll
+                for (int k = 0; k < NSTARS; k++) lnprior += lnp_eep[k];
+                lnprior += lnp_other;
+            }
+            lnprior += lnp_feh;
+            lnprior += lnp_dist;
+            lnprior += lnp_AV;
+        }
+        if (a.lnprior) a.lnprior[i] = lnprior;
+        const bool prior_ok = isfinite(lnprior);
+        if (!prior_ok && !a.lnlike) {
+            a.lnpost[i] = neg_inf;
+            continue;
+        }
+
+        // ---- lnlike -----------------------------------------------------------------------------------
+        double ll = 0.0;
+        if (m.spec_mask & 1) ll += iso_gauss(m.spec[0], Teff);
+        if (m.spec_mask & 2) ll += iso_gauss(m.spec[1], logg);
+        if (m.spec_mask & 4) ll += iso_gauss(m.spec[2], feh_s);
+        if (m.obs_mask) {
+            const double dist_mod = 5.0 * log10(dist / 10.0);   // mags.py:52
+            for (int ch = 0; ch < bc_chunks; ch++) {
+                const int cm = (m.obs_mask >> (4 * ch)) & 0xF;
+                if (!cm) continue;
+                double tot[4];
+                double flux[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < NSTARS; k++) {
+                    double mg4[4] = {nan, nan, nan, nan};
+                    if (bc_ok[k]) {
+                        unsigned node[16];
+                        double w[16];
+                        iso_corners<4>(bg, idx4[k], y4[k], node, w);
+                        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            iso_d4 q = iso_ldg256(bg.g + (size_t)node[j] * bg.ncols + 4 * ch);
+                            b0 = fma(q.x, w[j], b0);
+                            b1 = fma(q.y, w[j], b1);
+                            b2 = fma(q.z, w[j], b2);
+                            b3 = fma(q.w, w[j], b3);
+                        }
+                        const double mb = Mbol[k] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
+                        mg4[0] = mb - b0;
+                        mg4[1] = mb - b1;
+                        mg4[2] = mb - b2;
+                        mg4[3] = mb - b3;
+                    }
+                    if (NSTARS == 1) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) tot[b] = mg4[b];
+                    } else {   // fast_addmags utils.py:67-75 — only evaluated for observed columns
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (!(cm & (1 << b))) continue;
+                    if (NSTARS > 1) tot[b] = -2.5 * log10(flux[b]);
+                    ll += iso_gauss(m.mag[4 * ch + b], tot[b]);
+                }
+            }
+        }
+        if (m.has_plax) ll += iso_gauss(m.plax, 1000.0 / dist);   // starmodel.py:1599-1601
+        if (m.has_nu_max) {                                        // starmodel.py:1604-1612
+            ll += iso_gauss(m.nu_max, nu_max);
+            if (m.has_delta_nu) ll += iso_gauss(m.delta_nu, delta_nu);
+        }
+        if (a.lnlike) a.lnlike[i] = ll;
+        a.lnpost[i] = prior_ok ? lnprior + ll : neg_inf;   // starmodel.py:538-542
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static IsoGaussDev make_gauss(double val, double unc)
+{
+    IsoGaussDev g;
+    g.val = val;
+    g.c = ISO_LOG_ONE_OVER_ROOT_2PI + log(unc);
+    g.h = 1.0 / (unc * unc);
+    return g;
+}
+
+static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
+{
+    memset(&d, 0, sizeof(d));
+    ISO_REQUIRE(ctx, s.n_stars >= 1 && s.n_stars <= ISO_MAX_STARS, "iso_model: n_stars must be 1, 2 or 3");
+    ISO_REQUIRE(ctx, s.n_bands >= 0 && s.n_bands <= ISO_MAX_BANDS, "iso_model: too many bands");
+    d.n_stars = s.n_stars;
+    d.eep_replaces_age = s.eep_replaces_age ? 1 : 0;
+    int seen = 0;
+    for (int j = 0; j < 5; j++) {
+        ISO_REQUIRE(ctx, s.index_order[j] >= 0 && s.index_order[j] < 5, "iso_model: bad index_order");
+        seen |= 1 << s.index_order[j];
+        d.index_order[j] = s.index_order[j];
+    }
+    ISO_REQUIRE(ctx, seen == 31, "iso_model: index_order is not a permutation");
+    for (int i = 0; i < 3; i++) {
+        d.spec[i] = make_gauss(s.spec_val[i], s.spec_unc[i]);
+        if (s.spec_val[i] == s.spec_val[i]) d.spec_mask |= 1 << i;
+    }
+    for (int b = 0; b < s.n_bands; b++) {
+        int c = s.band_col[b];
+        ISO_REQUIRE(ctx, c >= 0 && c < ISO_MAX_BANDS, "iso_model: band_col out of range");
+        ISO_REQUIRE(ctx, !(d.obs_mask & (1 << c)), "iso_model: two bands map to the same BC-pack column");
+        d.obs_mask |= 1 << c;
+        d.mag[c] = make_gauss(s.mag_val[b], s.mag_unc[b]);
+    }
+    d.has_plax = s.has_plax ? 1 : 0;
+    d.has_nu_max = s.has_nu_max ? 1 : 0;
+    d.has_delta_nu = s.has_delta_nu ? 1 : 0;
+    d.plax = make_gauss(s.plax, s.plax_unc);
+    d.nu_max = make_gauss(s.nu_max, s.nu_max_unc);
+    d.delta_nu = make_gauss(s.delta_nu, s.delta_nu);   // the reference passes delta_nu as its own sigma (starmodel.py:1612)
+    d.eep_lo = s.eep_lo;
+    d.eep_hi = s.eep_hi;
+    d.eep_norm = s.eep_norm;
+    d.eep_has_bounds = s.eep_has_bounds ? 1 : 0;
+    const iso_prior *src[6] = {&s.eep_orig, &s.mass, &s.age, &s.feh, &s.distance, &s.AV};
+    iso_prior *dst[6] = {&d.eep_orig, &d.mass, &d.age, &d.feh, &d.distance, &d.AV};
+    for (int i = 0; i < 6; i++) {
+        // the prior of the parameter EEP replaces is only reached through eep_orig
+        bool used = !((i == 1 && !d.eep_replaces_age) || (i == 2 && d.eep_replaces_age));
+        *dst[i] = *src[i];
+        if (!used && !iso_prior_valid(*src[i])) {
+            memset(dst[i], 0, sizeof(iso_prior));
+            dst[i]->self.kind = ISO_PRIOR_FLAT;
+            continue;
+        }
+        ISO_REQUIRE(ctx, iso_prior_valid(*src[i]), "iso_model: unsupported prior kind (no CPU fallback exists)");
+        iso_prior_fill(dst[i]);
+    }
+    return ISO_OK;
+}
+
+static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, const iso_grid *bp, const iso_models *models,
+                         const int32_t *d_model_of_row, const double *d_pars, int64_t N, double *d_lnpost, double *d_lnprior,
+                         double *d_lnlike)
+{
+    IsoLnpostArgs a;
+    a.models = models->d_models;
+    a.model_of_row = d_model_of_row;
+    a.pars = d_pars;
+    a.lnpost = d_lnpost;
+    a.lnprior = d_lnprior;
+    a.lnlike = d_lnlike;
+    a.N = N;
+    int total = 0;
+    const iso_grid *gr[2] = {mp, bp};
+    for (int g = 0; g < 2; g++)
+        for (int d = 0; d < ISO_MAX_DIM; d++) {
+            a.smem_axis_off[g][d] = -1;   // closed-form axes need no table; iso_axis_locate never dereferences it
+            if (d >= gr[g]->dev.ndim || gr[g]->dev.ax[d].arith) continue;
+            a.smem_axis_off[g][d] = total;
+            total += gr[g]->dev.ax[d].n;
+        }
+    a.smem_nodes = total;
+    size_t smem = sizeof(double2) * (size_t)total + sizeof(IsoModelDev);
+    ISO_REQUIRE(ctx, smem <= 200 * 1024, "lnpost: axis tables do not fit in shared memory");
+    const bool catalog = d_model_of_row != nullptr;
+    int64_t want = (N + ISO_LNPOST_THREADS - 1) / ISO_LNPOST_THREADS;
+    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;
+    int blocks = (int)(want < cap ? want : cap);
+    if (blocks < 1) blocks = 1;
+#define ISO_LAUNCH(NS, CAT)                                                                                               \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024)                                                                                             \
+            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                               (int)smem));                                                               \
+        iso_lnpost_kernel<NS, CAT><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(mp->dev, bp->dev, a);                        \
+    } while (0)
+    switch (models->n_stars * 2 + (catalog ? 1 : 0)) {
+    case 2: ISO_LAUNCH(1, false); break;
+    case 3: ISO_LAUNCH(1, true); break;
+    case 4: ISO_LAUNCH(2, false); break;
+    case 5: ISO_LAUNCH(2, true); break;
+    case 6: ISO_LAUNCH(3, false); break;
+    case 7: ISO_LAUNCH(3, true); break;
+    default: return iso_set_error(ctx, ISO_E_INVALID, "lnpost: bad n_stars");
+    }
+#undef ISO_LAUNCH
+    ctx->launches++;
+    ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+static int check_lnpost_args(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, const iso_models *models)
+{
+    ISO_REQUIRE(ctx, mp && bp && models, "lnpost: NULL handle");
+    ISO_REQUIRE(ctx, mp->device == ctx->device && bp->device == ctx->device && models->device == ctx->device,
+                "lnpost: handle belongs to another device");
+    ISO_REQUIRE(ctx, mp->dev.ndim == 3 && mp->dev.ncols == ISO_MP_NCOLS,
+                "lnpost: model_pack must be a 3-D grid with the 8 ISO_MP_* columns (iso_grid_repack)");
+    ISO_REQUIRE(ctx, bp->dev.ndim == 4 && bp->dev.ncols % 4 == 0 && bp->dev.ncols <= ISO_MAX_BANDS,
+                "lnpost: bc_pack must be a 4-D grid with 4, 8, 12 or 16 columns (iso_grid_repack)");
+    ISO_REQUIRE(ctx, models->max_col < bp->dev.ncols, "lnpost: a model observes a band column the BC pack does not have");
+    return ISO_OK;
+}
+
+struct LnpostUser {
+    const iso_grid *mp, *bp;
+    const iso_models *models;
+    bool catalog, want_prior, want_like;
+};
+
+static int lnpost_pipe_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    (void)row0;
+    LnpostUser *u = (LnpostUser *)user;
+    return lnpost_launch(ctx, st, u->mp, u->bp, u->models, u->catalog ? (const int32_t *)d[1] : nullptr, (const double *)d[0],
+                         n, (double *)d[2], u->want_prior ? (double *)d[3] : nullptr, u->want_like ? (double *)d[4] : nullptr);
+}
+
+__global__ void iso_mnest_prior_kernel(double *cube, const double *lo, const double *hi, int ndim, long long total)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(t % ndim);
+        cube[t] = __dadd_rn(__dmul_rn(hi[j] - lo[j], cube[t]), lo[j]);   // starmodel.py:1637-1640 (unfused, bit-exact)
+    }
+}
+
+struct MnestUser {
+    const double *d_lo, *d_hi;
+    int ndim;
+};
+
+static int mnest_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    (void)row0;
+    MnestUser *u = (MnestUser *)user;
+    long long total = n * u->ndim;
+    int blocks = (int)((total + 255) / 256 < ctx->prop.multiProcessorCount * 8 ? (total + 255) / 256
+                                                                                : ctx->prop.multiProcessorCount * 8);
+    // in place: the output array aliases the input rows (d[1] receives a device-side copy below)
+    ISO_CUDA(ctx, cudaMemcpyAsync(d[1], d[0], (size_t)total * 8, cudaMemcpyDeviceToDevice, st));
+    iso_mnest_prior_kernel<<<blocks, 256, 0, st>>>((double *)d[1], u->d_lo, u->d_hi, u->ndim, total);
+    ctx->launches++;
+    ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+extern "C" {
+
+int iso_models_stage(iso_ctx *ctx, const iso_model *h_models, int n_models, iso_models **out)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_models_stage: ctx is NULL");
+    ISO_REQUIRE(ctx, h_models && out && n_models >= 1, "iso_models_stage: bad argument");
+    *out = nullptr;
+    std::vector<IsoModelDev> dev((size_t)n_models);
+    int max_col = -1;
+    bool seismo = false;
+    for (int i = 0; i < n_models; i++) {
+        int rc = convert_model(ctx, h_models[i], dev[i]);
+        if (rc != ISO_OK) return rc;
+        ISO_REQUIRE(ctx, dev[i].n_stars == dev[0].n_stars, "iso_models_stage: all models must share n_stars");
+        for (int c = 0; c < ISO_MAX_BANDS; c++)
+            if (dev[i].obs_mask & (1 << c)) max_col = c > max_col ? c : max_col;
+        seismo = seismo || dev[i].has_nu_max;
+    }
+    IsoDeviceGuard guard(ctx->device);
+    iso_models *m = new iso_models();
+    m->n_models = n_models;
+    m->n_stars = dev[0].n_stars;
+    m->device = ctx->device;
+    m->max_col = max_col;
+    m->needs_seismo = seismo;
+    cudaError_t e = cudaMalloc(&m->d_models, sizeof(IsoModelDev) * (size_t)n_models);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->d_models, dev.data(), sizeof(IsoModelDev) * (size_t)n_models, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (m->d_models) cudaFree(m->d_models);
+        delete m;
+        return iso_check_cuda(ctx, e, "iso_models_stage");
+    }
+    *out = m;
+    return ISO_OK;
+}
+
+int iso_models_destroy(iso_ctx *ctx, iso_models *models)
+{
+    if (!models) return ISO_OK;
+    IsoDeviceGuard guard(models->device);
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (models->d_models) cudaFree(models->d_models);
+    delete models;
+    return ISO_OK;
+}
+
+int iso_lnpost_batch_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                            const int32_t *d_model_of_row, const double *d_pars, int64_t N, double *d_lnpost,
+                            double *d_lnprior, double *d_lnlike)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_lnpost_batch_device: ctx is NULL");
+    int rc = check_lnpost_args(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0, "lnpost: negative N");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, d_pars && d_lnpost, "lnpost: NULL buffer");
+    ISO_REQUIRE(ctx, d_model_of_row || models->n_models == 1, "lnpost: several models staged but no model_of_row given");
+    IsoDeviceGuard guard(ctx->device);
+    return lnpost_launch(ctx, ctx->stream, model_pack, bc_pack, models, d_model_of_row, d_pars, N, d_lnpost, d_lnprior,
+                         d_lnlike);
+}
+
+int iso_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                     const int32_t *h_model_of_row, const double *h_pars, int64_t N, double *h_lnpost, double *h_lnprior,
+                     double *h_lnlike)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_lnpost_batch: ctx is NULL");
+    int rc = check_lnpost_args(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0, "lnpost: negative N");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_pars && h_lnpost, "lnpost: NULL buffer");
+    ISO_REQUIRE(ctx, h_model_of_row || models->n_models == 1, "lnpost: several models staged but no model_of_row given");
+    if (h_model_of_row)
+        for (int64_t i = 0; i < N; i++)
+            ISO_REQUIRE(ctx, h_model_of_row[i] >= 0 && h_model_of_row[i] < models->n_models, "lnpost: model_of_row out of range");
+    int ndim = 4 + models->n_stars;
+    IsoPipeArray arr[5];
+    arr[0] = IsoPipeArray{h_pars, nullptr, (int64_t)8 * ndim};
+    arr[1] = IsoPipeArray{h_model_of_row, nullptr, 4};
+    arr[2] = IsoPipeArray{nullptr, h_lnpost, 8};
+    arr[3] = IsoPipeArray{nullptr, h_lnprior, 8};
+    arr[4] = IsoPipeArray{nullptr, h_lnlike, 8};
+    LnpostUser u{model_pack, bc_pack, models, h_model_of_row != nullptr, h_lnprior != nullptr, h_lnlike != nullptr};
+    return iso_run_pipeline(ctx, N, arr, 5, lnpost_pipe_launch, &u);
+}
+
+int iso_mnest_prior(iso_ctx *ctx, const double *h_lo, const double *h_hi, int ndim, double *h_cube, int64_t N)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_mnest_prior: ctx is NULL");
+    ISO_REQUIRE(ctx, h_lo && h_hi && ndim >= 1 && ndim <= 64 && N >= 0, "iso_mnest_prior: bad argument");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_cube, "iso_mnest_prior: cube is NULL");
+    IsoDeviceGuard guard(ctx->device);
+    double *d_b = nullptr;
+    ISO_CUDA(ctx, cudaMalloc(&d_b, sizeof(double) * 2 * ndim));
+    cudaError_t e = cudaMemcpy(d_b, h_lo, sizeof(double) * ndim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_b + ndim, h_hi, sizeof(double) * ndim, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_b);
+        return iso_check_cuda(ctx, e, "iso_mnest_prior");
+    }
+    // input and output are the same host array: two pipeline arrays over it (read, then write back)
+    IsoPipeArray arr[2];
+    arr[0] = IsoPipeArray{h_cube, nullptr, (int64_t)8 * ndim};
+    arr[1] = IsoPipeArray{nullptr, h_cube, (int64_t)8 * ndim};
+    MnestUser u{d_b, d_b + ndim, ndim};
+    int rc = iso_run_pipeline(ctx, N, arr, 2, mnest_launch, &u);
+    cudaFree(d_b);
+    return rc;
+}
+
+}  // extern "C"

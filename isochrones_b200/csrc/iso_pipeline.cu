@@ -1,0 +1,107 @@
+// isochrones_b200 — chunked host<->device pipeline behind the host-pointer entry points of the C ABI.
+//
+// A batch of N rows is cut into chunks; chunk c runs H2D -> kernel -> D2H in order on copy_stream[c & 1], so the
+// PCIe transfers of one chunk overlap the kernel (and the opposite-direction transfer) of the other.
+#include <string.h>
+
+#include "iso_common.cuh"
+
+#define ISO_PIPE_CHUNK_ROWS (1 << 18)
+
+static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+struct PipeSlot {
+    int64_t row0 = 0, n = 0;
+    bool busy = false;
+};
+
+int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, int n_arrays, iso_pipe_launch_fn launch,
+                     void *user)
+{
+    ISO_REQUIRE(ctx, n_arrays >= 1 && n_arrays <= ISO_PIPE_MAX_ARRAYS, "pipeline: bad array count");
+    if (n_rows <= 0) return ISO_OK;
+    IsoDeviceGuard guard(ctx->device);
+
+    int64_t chunk = n_rows < ISO_PIPE_CHUNK_ROWS ? n_rows : ISO_PIPE_CHUNK_ROWS;
+    int64_t off[ISO_PIPE_MAX_ARRAYS + 1];
+    bool pinned[ISO_PIPE_MAX_ARRAYS];
+    bool active[ISO_PIPE_MAX_ARRAYS];
+    off[0] = 0;
+    bool any_pageable = false;
+    for (int k = 0; k < n_arrays; k++) {
+        const void *h = arrays[k].h_in ? arrays[k].h_in : arrays[k].h_out;
+        active[k] = (h != nullptr);
+        pinned[k] = active[k] && is_pinned(h);
+        if (active[k] && !pinned[k]) any_pageable = true;
+        off[k + 1] = off[k] + (active[k] ? align256(chunk * arrays[k].row_bytes) : 0);
+    }
+    int n_slots = n_rows > chunk ? 2 : 1;
+    for (int s = 0; s < n_slots; s++) {
+        int rc = iso_stage_reserve(ctx, s, off[n_arrays], any_pageable ? off[n_arrays] : 0);
+        if (rc != ISO_OK) return rc;
+    }
+    // everything queued on the compute stream so far (grid staging, device-API calls) happens-before the pipeline
+    ISO_CUDA(ctx, cudaEventRecord(ctx->ev_copy[0], ctx->stream));
+    for (int s = 0; s < n_slots; s++) ISO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream[s], ctx->ev_copy[0], 0));
+
+    PipeSlot slots[2];
+    auto finalize = [&](int s) -> int {
+        if (!slots[s].busy) return ISO_OK;
+        ISO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[s]));
+        for (int k = 0; k < n_arrays; k++) {
+            if (!active[k] || pinned[k] || !arrays[k].h_out) continue;
+            memcpy((char *)arrays[k].h_out + slots[s].row0 * arrays[k].row_bytes, (char *)ctx->h_stage[s] + off[k],
+                   (size_t)(slots[s].n * arrays[k].row_bytes));
+        }
+        slots[s].busy = false;
+        return ISO_OK;
+    };
+
+    int c = 0;
+    for (int64_t row0 = 0; row0 < n_rows; row0 += chunk, c++) {
+        int s = c & (n_slots - 1);
+        int64_t n = n_rows - row0 < chunk ? n_rows - row0 : chunk;
+        int rc = finalize(s);
+        if (rc != ISO_OK) return rc;
+        cudaStream_t st = ctx->copy_stream[s];
+        void *d_arrays[ISO_PIPE_MAX_ARRAYS];
+        for (int k = 0; k < n_arrays; k++) {
+            d_arrays[k] = active[k] ? (void *)((char *)ctx->d_stage[s] + off[k]) : nullptr;
+            if (!active[k] || !arrays[k].h_in) continue;
+            const char *src = (const char *)arrays[k].h_in + row0 * arrays[k].row_bytes;
+            size_t bytes = (size_t)(n * arrays[k].row_bytes);
+            if (!pinned[k]) {
+                memcpy((char *)ctx->h_stage[s] + off[k], src, bytes);
+                src = (const char *)ctx->h_stage[s] + off[k];
+            }
+            ISO_CUDA(ctx, cudaMemcpyAsync(d_arrays[k], src, bytes, cudaMemcpyHostToDevice, st));
+        }
+        rc = launch(ctx, st, d_arrays, row0, n, user);
+        if (rc != ISO_OK) return rc;
+        for (int k = 0; k < n_arrays; k++) {
+            if (!active[k] || !arrays[k].h_out) continue;
+            size_t bytes = (size_t)(n * arrays[k].row_bytes);
+            char *dst = pinned[k] ? (char *)arrays[k].h_out + row0 * arrays[k].row_bytes : (char *)ctx->h_stage[s] + off[k];
+            ISO_CUDA(ctx, cudaMemcpyAsync(dst, d_arrays[k], bytes, cudaMemcpyDeviceToHost, st));
+        }
+        slots[s].row0 = row0;
+        slots[s].n = n;
+        slots[s].busy = true;
+    }
+    for (int s = 0; s < n_slots; s++) {
+        int rc = finalize(s);
+        if (rc != ISO_OK) return rc;
+    }
+    return ISO_OK;
+}

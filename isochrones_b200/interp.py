@@ -1,0 +1,113 @@
+"""``DFInterpolator`` — drop-in for the reference's ``isochrones/interp.py:571-698`` with the interpolation
+running on the GPU.
+
+Same constructor arguments, attributes (``grid``, ``index_columns``, ``columns``, ``column_index``,
+``n_columns``, ``ndim``, ``index_names``) and call convention: ``interp(p, cols)`` with all-scalar ``p``
+returns a 1-D array of ``len(cols)`` values, anything else is broadcast and returns ``(N, ncols)``
+(interp.py:631-698).  ``NaN`` means "outside the grid".  The dense grid is staged once to HBM on first use;
+each call is one CUDA launch (``iso_interp_values`` replaces ``interp_value(s)_{2,3,4}d``).
+"""
+import itertools
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+class DFInterpolator(object):
+    """Interpolate column values of a DataFrame with a full-grid hierarchical index (interp.py:571-614)."""
+
+    def __init__(self, df, filename=None, recalc=False, is_full=False, ctx=None):
+        self.filename = filename
+        self.is_full = is_full
+        self.columns = list(df.columns)
+        self.n_columns = len(self.columns)
+        self.grid = self._make_grid(df, recalc=recalc)
+        self.index_columns = tuple(np.array(l, dtype=float) for l in df.index.levels)
+        self.index_names = df.index.names
+        self.ndim = len(self.index_columns)
+        self.column_index = {c: self.columns.index(c) for c in self.columns}
+        self._ctx = ctx
+        self._device_grid = None
+
+    @classmethod
+    def from_arrays(cls, grid, index_columns, columns, index_names=None, ctx=None):
+        """Build directly from a dense ``grid[n0, .., ncols]`` and its axes (no DataFrame round trip)."""
+        self = cls.__new__(cls)
+        self.filename = None
+        self.is_full = True
+        self.columns = [str(c) for c in columns]
+        self.n_columns = len(self.columns)
+        self.grid = np.ascontiguousarray(grid, dtype=float)
+        self.index_columns = tuple(np.array(a, dtype=float) for a in index_columns)
+        self.index_names = list(index_names) if index_names is not None else [None] * len(self.index_columns)
+        self.ndim = len(self.index_columns)
+        self.column_index = {c: i for i, c in enumerate(self.columns)}
+        assert self.grid.shape == tuple(len(a) for a in self.index_columns) + (self.n_columns,)
+        self._ctx = ctx
+        self._device_grid = None
+        return self
+
+    def _make_grid(self, df, recalc=False):
+        # host-side, one-time data preparation (interp.py:590-614): NaN-pad a non-full index to a dense array
+        if self.filename is not None and os.path.exists(self.filename) and not recalc:
+            d = np.load(self.filename)
+            grid = d["grid"]
+            columns = d["columns"]
+            if not all(columns == self.columns):
+                raise ValueError("DataFrame columns do not match columns loaded from full grid!")
+        else:
+            import pandas as pd
+
+            if not self.is_full:
+                idx = pd.MultiIndex.from_tuples([ixs for ixs in itertools.product(*df.index.levels)])
+                grid_df = pd.DataFrame(index=idx, columns=df.columns, dtype=float)
+                grid_df.loc[df.index] = df
+            else:
+                grid_df = df
+            shape = [len(l) for l in df.index.levels] + [len(df.columns)]
+            grid = np.array(grid_df.values, dtype=float).reshape(shape)
+            if self.filename is not None:
+                np.savez(self.filename, grid=grid, columns=self.columns)
+        return grid
+
+    # ---- device residency -------------------------------------------------------------------------------
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    @property
+    def device_grid(self):
+        """The grid staged in HBM (created on first use; dropped by ``add_column``)."""
+        if self._device_grid is None:
+            self._device_grid = _lib.DeviceGrid(self.ctx, self.grid, self.index_columns)
+        return self._device_grid
+
+    def add_column(self, values, name):
+        newgrid = np.empty((self.grid.shape[:-1]) + (self.n_columns + 1,))
+        newgrid[..., :-1] = self.grid
+        newgrid[..., -1] = values
+        self.column_index[name] = self.n_columns
+        self.n_columns += 1
+        self.columns += [name]
+        self.grid = newgrid
+        self._device_grid = None
+
+    def __call__(self, p, cols="all"):
+        if isinstance(cols, str) and cols == "all":
+            icols = np.arange(self.n_columns)
+        else:
+            icols = np.array([self.column_index[col] for col in cols])
+        if len(p) != self.ndim:
+            raise ValueError("expected %d coordinates, got %d" % (self.ndim, len(p)))
+        scalar = all(isinstance(x, (float, int)) for x in p)     # interp.py:638-666 (np.float64 is a float)
+        if scalar:
+            pp = [np.array([x], dtype=float) for x in p]
+        else:
+            b = np.broadcast(*p)
+            pp = [np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel() for x in p]
+        values = self.device_grid.interp_values(pp, icols)
+        return values[0] if scalar else values

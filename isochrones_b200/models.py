@@ -1,0 +1,297 @@
+"""``ModelGridInterpolator`` / ``EvolutionTrackInterpolator`` / ``IsochroneInterpolator`` — host-side mirror of
+the part of the reference's ``isochrones/models.py:253-718`` that sits on the lnpost path.
+
+Kept from the reference: ``param_names``, ``eep_replaces``, ``param_index_order`` (models.py:259, 665-669,
+692-696), ``bands``, ``model_grid`` / ``bc_grid`` objects exposing ``.interp`` (a ``DFInterpolator``),
+``.get_limits(prop)`` and ``.bands``, ``interp_value(pars, props)`` (models.py:390-400), ``interp_mag(pars,
+bands)`` (:402-445), ``initialize`` (:349-358) and the property shortcuts (``mass``, ``radius``, ``Teff`` ...).
+
+Out of scope: grid download / parsing (``Grid``, ``StellarModelGrid``, ``MIST*Grid``).  The grids
+come in as dense arrays — synthetic MIST-shaped ones from :mod:`isochrones_b200.synthetic`, or the reference's own
+cached ``.npz`` dense grids through :func:`isochrones_b200.loaders` — and are staged once to HBM.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .interp import DFInterpolator
+
+MODEL_PACK_COLUMNS = ("Teff", "logg", "feh", "Mbol", None, None, "nu_max", "delta_nu")   # ISO_MP_* order
+
+
+class ModelGrid(object):
+    """Minimal stand-in for the reference's ``StellarModelGrid`` objects: a dense interpolator + limits."""
+
+    def __init__(self, interp, limits, eep_replaces, name="grid"):
+        self.interp = interp
+        self._limits = dict(limits)
+        self.eep_replaces = eep_replaces
+        self.name = name
+
+    def get_limits(self, prop):
+        return self._limits[prop]          # reference grid.py:58-61 / mist/models.py:37
+
+    @property
+    def fehs(self):
+        i = 0 if self.eep_replaces == "age" else 1
+        return self.interp.index_columns[i]
+
+    @property
+    def masses(self):
+        return self.interp.index_columns[1]
+
+    @property
+    def ages(self):
+        return self.interp.index_columns[0]
+
+
+class BCGrid(object):
+    """Stand-in for ``BolometricCorrectionGrid`` (bc.py): 4-D interpolator over (Teff, logg, [Fe/H], Av)."""
+
+    def __init__(self, interp, bands=None):
+        self.interp = interp
+        self.bands = list(bands) if bands is not None else list(interp.columns)
+
+
+class ModelGridInterpolator(object):
+    # transformation from desired param order to that expected by interp functions (models.py:259)
+    _param_index_order = (1, 2, 0, 3, 4)
+    eep_bounds = (0, 1710)        # mist/isochrone.py:9, 21
+    eep_replaces = None
+    param_names = None
+
+    def __init__(self, model_grid, bc_grid, bands=None, eep_bounds=None, ctx=None, **kwargs):
+        self.bands = list(bands) if bands is not None else list(bc_grid.bands)
+        self._model_grid = model_grid
+        self._bc_grid = bc_grid
+        self.param_index_order = list(self._param_index_order)
+        self.kwargs = kwargs
+        if eep_bounds is not None:
+            self.eep_bounds = tuple(eep_bounds)
+        self._ctx = ctx
+        self._model_pack = None
+        self._bc_packs = {}
+
+    # ---- reference attribute surface -----------------------------------------------------------------------
+    @property
+    def model_grid(self):
+        return self._model_grid
+
+    @property
+    def bc_grid(self):
+        return self._bc_grid
+
+    @property
+    def name(self):
+        return self.model_grid.name
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    def _limit(self, prop, i):
+        return self.model_grid.get_limits(prop)[i]
+
+    minfeh = property(lambda self: self._limit("feh", 0))
+    maxfeh = property(lambda self: self._limit("feh", 1))
+    mineep = property(lambda self: self._limit("eep", 0))
+    maxeep = property(lambda self: self._limit("eep", 1))
+    minage = property(lambda self: self._limit("age", 0))
+    maxage = property(lambda self: self._limit("age", 1))
+    minmass = property(lambda self: self._limit("mass", 0))
+    maxmass = property(lambda self: self._limit("mass", 1))
+
+    @property
+    def fehs(self):
+        return self.model_grid.fehs
+
+    def initialize(self, pars=None):
+        if pars is None:
+            if self.eep_replaces == "age":
+                pars = [1.04, 320.0, -0.35, 10000.0, 0.34]
+            elif self.eep_replaces == "mass":
+                pars = [320, 9.7, -0.35, 10000.0, 0.34]
+        Teff, logg, feh, mags = self.interp_mag(pars, self.bands)
+        assert all([np.isfinite(v) for v in [Teff, logg, feh]])
+        assert all([np.isfinite(m) for m in mags])
+
+    def _prop(self, prop, *pars):
+        return self.interp_value(pars, [prop]).squeeze()
+
+    def mass(self, *pars):
+        return self._prop("mass", *pars)
+
+    def initial_mass(self, *pars):
+        return self._prop("initial_mass", *pars)
+
+    def radius(self, *pars):
+        return self._prop("radius", *pars)
+
+    def Teff(self, *pars):
+        return self._prop("Teff", *pars)
+
+    def logg(self, *pars):
+        return self._prop("logg", *pars)
+
+    def feh(self, *pars):
+        return self._prop("feh", *pars)
+
+    def density(self, *pars):
+        return self._prop("density", *pars)
+
+    def nu_max(self, *pars):
+        return self._prop("nu_max", *pars)
+
+    def delta_nu(self, *pars):
+        return self._prop("delta_nu", *pars)
+
+    # ---- device-resident packs the fused kernels gather from ---------------------------------------------------
+    @property
+    def model_pack(self):
+        """8-column pack (Teff, logg, feh, Mbol, orig, deriv, nu_max, delta_nu), one 64-byte node per grid point."""
+        if self._model_pack is None:
+            ci = self.model_grid.interp.column_index
+            orig, deriv = ("age", "dt_deep") if self.eep_replaces == "age" else ("mass", "dm_deep")
+            names = ["Teff", "logg", "feh", "Mbol", orig, deriv, "nu_max", "delta_nu"]
+            for n in names[:6]:
+                if n not in ci:
+                    raise KeyError("model grid lacks column %r needed by the lnpost path" % n)
+            cols = [ci.get(n, -1) for n in names]
+            interp = self.model_grid.interp
+            if interp._device_grid is not None:
+                self._model_pack = interp.device_grid.repack(cols, _lib.ISO_MP_NCOLS)
+            else:
+                # build the pack on the host so the full (18-column) grid never has to occupy HBM
+                g = interp.grid
+                pack = np.zeros(g.shape[:-1] + (_lib.ISO_MP_NCOLS,))
+                for j, c in enumerate(cols):
+                    if c >= 0:
+                        pack[..., j] = g[..., c]
+                self._model_pack = _lib.DeviceGrid(self.ctx, pack, interp.index_columns)
+        return self._model_pack
+
+    def bc_pack(self, bands):
+        """(device grid, column of each band) holding ``bands`` padded to a multiple of 4 columns (32-byte sectors)."""
+        key = tuple(bands)
+        if key not in self._bc_packs:
+            interp = self.bc_grid.interp
+            cols = [interp.column_index[b] for b in key] or [0]
+            if len(cols) > _lib.ISO_MAX_BANDS:
+                raise ValueError("at most %d bands per star model" % _lib.ISO_MAX_BANDS)
+            ncols_out = 4 * ((len(cols) + 3) // 4)
+            g = interp.grid
+            pack = np.zeros(g.shape[:-1] + (ncols_out,))
+            for j, c in enumerate(cols):
+                pack[..., j] = g[..., c]
+            self._bc_packs[key] = _lib.DeviceGrid(self.ctx, pack, interp.index_columns)
+        return self._bc_packs[key]
+
+    # ---- the hot entry points -----------------------------------------------------------------------------
+    def interp_value(self, pars, props):
+        """pars : (mass, eep, feh[, distance, AV]) for tracks / (eep, age, feh[, ..]) for isochrones
+        (models.py:390-400); scalars give ``[len(props)]``, arrays ``[N, len(props)]``."""
+        i0, i1, i2 = self.param_index_order[:3]
+        try:
+            pars = np.atleast_1d(pars[self.param_index_order])
+            p = [pars[0], pars[1], pars[2]]
+            if pars.ndim == 1:
+                p = [float(v) for v in p]
+        except (TypeError, IndexError):
+            p = [pars[i0], pars[i1], pars[i2]]
+        if isinstance(props, str):
+            props = [props]
+        return self.model_grid.interp(p, props)
+
+    def interp_mag(self, pars, bands):
+        """pars : five parameters in ``param_names`` order; returns ``(Teff, logg, feh, mags)`` — scalars and a
+        ``[n_bands]`` array for a single point, ``[N]`` arrays and ``[N, n_bands]`` otherwise (models.py:402-445)."""
+        bands = list(bands) if bands is not None else []
+        scalar = False
+        try:
+            p = np.atleast_1d(pars).astype(float).squeeze()
+            if p.ndim > 1 or p.shape != (5,):
+                raise ValueError
+            scalar = True
+            p = p.reshape(5, 1)
+        except (TypeError, ValueError):
+            b = np.broadcast(*pars)
+            p = np.array([np.resize(x, b.shape).astype(float).ravel() for x in pars])
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        n = p.shape[1]
+        bc, = (self.bc_pack(bands),)
+        teff, logg, feh = np.empty(n), np.empty(n), np.empty(n)
+        mags = np.empty((n, len(bands)))
+        io = np.array(self.param_index_order, dtype=np.int32)
+        bc_cols = np.arange(len(bands), dtype=np.int32)
+        ctx = self.ctx
+        ctx.check(_lib.lib().iso_interp_mags(
+            ctx.handle, self.model_pack.handle, bc.handle, _lib.ip(io), 0, 1, 2, 3, _lib.ip(bc_cols), len(bands),
+            _lib.dp(p), n, _lib.dp(teff), _lib.dp(logg), _lib.dp(feh), _lib.dp(mags)))
+        if scalar:
+            return float(teff[0]), float(logg[0]), float(feh[0]), mags[0]
+        return teff, logg, feh, mags
+
+    def __call__(self, p1, p2, p3, distance=10.0, AV=0.0):
+        """All model-grid columns + magnitudes as a DataFrame (models.py:471-482) — same kernels, wider output."""
+        import pandas as pd
+
+        p1, p2, p3, dist, AV = [np.atleast_1d(a).astype(float).ravel()
+                                for a in np.broadcast_arrays(p1, p2, p3, distance, AV)]
+        pars = [p1, p2, p3, dist, AV]
+        prop_cols = list(self.model_grid.interp.columns)
+        props = self.interp_value(pars, prop_cols)
+        _, _, _, mags = self.interp_mag(pars, self.bands)
+        cols = prop_cols + ["{}_mag".format(b) for b in self.bands]
+        values = np.concatenate([np.atleast_2d(props), np.atleast_2d(mags)], axis=1)
+        return pd.DataFrame(values, columns=cols)
+
+
+class EvolutionTrackInterpolator(ModelGridInterpolator):
+    param_names = ("mass", "eep", "feh", "distance", "AV")      # models.py:665
+    eep_replaces = "age"
+    _param_index_order = (2, 0, 1, 3, 4)                         # models.py:669
+
+
+class IsochroneInterpolator(ModelGridInterpolator):
+    param_names = ("eep", "age", "feh", "distance", "AV")       # models.py:692
+    eep_replaces = "mass"
+    _param_index_order = (1, 2, 0, 3, 4)                         # models.py:696
+
+
+def _from_synthetic(cls, model, bc, bands=None, eep_bounds=None, ctx=None):
+    mi = DFInterpolator.from_arrays(model["grid"], model["axes"], model["columns"], ctx=ctx)
+    bi = DFInterpolator.from_arrays(bc["grid"], bc["axes"], bc["columns"], ctx=ctx)
+    replaces = cls.eep_replaces
+    mg = ModelGrid(mi, model["limits"], replaces, name="synthetic_" + model.get("kind", "grid"))
+    if eep_bounds is None:
+        eep_bounds = tuple(model["limits"]["eep"])
+    return cls(mg, BCGrid(bi, bc["columns"]), bands=bands, eep_bounds=eep_bounds, ctx=ctx)
+
+
+def ichrone_from_arrays(kind, model, bc, bands=None, eep_bounds=None, ctx=None):
+    """Interpolator over in-memory dense grids: ``model`` / ``bc`` are dicts with ``grid``, ``axes``, ``columns``
+    (+ ``limits`` for the model grid), e.g. from :mod:`isochrones_b200.synthetic`; ``kind`` is "track" or "iso"."""
+    cls = EvolutionTrackInterpolator if kind == "track" else IsochroneInterpolator
+    return _from_synthetic(cls, model, bc, bands=bands, eep_bounds=eep_bounds, ctx=ctx)
+
+
+def get_ichrone(models="mist", bands=None, tracks=False, synthetic_shape=None, ctx=None, **kwargs):
+    """``get_ichrone`` of the reference (isochrone.py:47-78) for the one grid family on the path (MIST).
+
+    No MIST data can exist in this environment (no network), so the grids are the deterministic MIST-*shaped*
+    synthetic ones; ``synthetic_shape`` (dict of ``make_*_grid`` keyword arguments) shrinks them for tests."""
+    from . import synthetic as syn
+
+    if not (isinstance(models, str) and models.lower().startswith("mist")):
+        raise ValueError("only the MIST grid family is on the accelerated path")
+    bands = list(bands) if bands is not None else ["G", "BP", "RP", "J", "H", "K", "W1", "W2", "W3", "TESS", "Kepler"]
+    shape = dict(synthetic_shape or {})
+    bc = syn.make_bc_grid(bands=tuple(bands), **shape.get("bc", {}))
+    if tracks:
+        model = syn.make_track_grid(**shape.get("track", {}))
+        return ichrone_from_arrays("track", model, bc, bands=bands, ctx=ctx)
+    model = syn.make_iso_grid(**shape.get("iso", {}))
+    return ichrone_from_arrays("iso", model, bc, bands=bands, ctx=ctx)

@@ -1,0 +1,373 @@
+"""``BasicStarModel`` (+ ``SingleStarModel`` / ``BinaryStarModel`` / ``TripleStarModel``) — drop-in for the lnpost
+path of the reference's ``isochrones/starmodel.py:1361-2007``.
+
+Same constructor keywords, ``param_names``, ``bands``, ``spec_props``, ``bounds``, ``set_prior``, ``set_bounds``,
+``lnprior(p)``, ``lnlike(p)``, ``lnpost(p)``, ``mnest_prior``, ``mnest_loglike`` and ``sample_from_prior``.  The
+scalar calls are batches of one; ``lnpost_batch(P[N, ndim])`` is the new batched entry the samplers should use:
+one fused CUDA launch per batch (``iso_lnpost_batch``).  The observation tuples and the prior objects are
+compiled once into a device struct (``iso_model``) and re-compiled only when ``set_prior`` / ``set_bounds`` change
+them.  Priors the device cannot evaluate raise at compile time — there is no CPU fallback.
+
+Out of scope: ini parsing, HDF save/load, corner plots, the obs-tree ``StarModel``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .priors import AgePrior, AVPrior, ChabrierPrior, DistancePrior, EEP_prior, FehPrior
+
+
+class CompiledModel(object):
+    """Device image of one or more star models that share an interpolator (catalog mode: one per star)."""
+
+    def __init__(self, ic, structs, bands_key):
+        self.ic = ic
+        self.ctx = ic.ctx
+        self.n_models = len(structs)
+        self.n_stars = structs[0].n_stars
+        self.ndim = 4 + self.n_stars
+        self.model_pack = ic.model_pack
+        self.bc_pack = ic.bc_pack(bands_key)
+        arr = (_lib.IsoModel * len(structs))(*structs)
+        self.handle = C.c_void_p()
+        self.ctx.check(_lib.lib().iso_models_stage(self.ctx.handle, arr, len(structs), C.byref(self.handle)))
+
+    def lnpost(self, pars, parts=False, model_of_row=None, out=None):
+        """``pars[N, ndim]`` -> ``lnpost[N]`` (and ``lnprior[N]``, ``lnlike[N]`` when ``parts``)."""
+        pars = np.asarray(pars)
+        if pars.dtype != np.float64 or not pars.flags["C_CONTIGUOUS"]:
+            pars = np.ascontiguousarray(pars, dtype=np.float64)
+        if pars.ndim != 2 or pars.shape[1] != self.ndim:
+            raise ValueError("expected pars of shape [N, %d], got %r" % (self.ndim, pars.shape))
+        n = pars.shape[0]
+        lnpost = out if out is not None else np.empty(n)
+        mor = None
+        if model_of_row is not None:
+            mor = np.ascontiguousarray(model_of_row, dtype=np.int32)
+            assert mor.shape == (n,)
+        elif self.n_models != 1:
+            raise ValueError("model_of_row is required when several models are compiled together")
+        lnprior = np.empty(n) if parts else None
+        lnlike = np.empty(n) if parts else None
+        self.ctx.check(_lib.lib().iso_lnpost_batch(
+            self.ctx.handle, self.model_pack.handle, self.bc_pack.handle, self.handle,
+            _lib.ip(mor) if mor is not None else None, _lib.dp(pars), n, _lib.dp(lnpost),
+            _lib.dp(lnprior) if parts else None, _lib.dp(lnlike) if parts else None))
+        if parts:
+            return lnpost, lnprior, lnlike
+        return lnpost
+
+    def close(self):
+        if self.handle:
+            _lib.lib().iso_models_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BasicStarModel(object):
+    """Bare-bones star model without the observation-tree machinery (starmodel.py:1361-1989)."""
+
+    use_emcee = False
+    _not_a_band = ("RA", "dec", "ra", "Dec", "maxAV", "parallax", "AV", "logg", "Teff", "feh", "density",
+                   "separation", "PA", "resolution", "relative", "N", "index", "id", "nu_max", "delta_nu")
+
+    def __init__(self, ic, eep_bounds=None, name="", directory=".", N=1, maxAV=None, max_distance=None,
+                 halo_fraction=None, ra=None, dec=None, obs=None, use_emcee=False, **kwargs):
+        self._ic = ic
+        self.eep_bounds = eep_bounds if eep_bounds is not None else self.ic.eep_bounds
+        self.name = str(name)
+        self.use_emcee = use_emcee
+        self.ra = ra
+        self.dec = dec
+        self.obs = None
+
+        if N > 1 and ic.eep_replaces == "age":
+            raise ValueError("Can only fit mulitple stars with IsochroneInterpolator!")
+        if N == 1:
+            if ic.eep_replaces == "age":
+                self.mass_index, self.feh_index, self.distance_index, self.AV_index = 0, 2, 3, 4
+            elif ic.eep_replaces == "mass":
+                self.age_index, self.feh_index, self.distance_index, self.AV_index = 1, 2, 3, 4
+        elif N == 2:
+            self.age_index, self.feh_index, self.distance_index, self.AV_index = 2, 3, 4, 5
+        elif N == 3:
+            self.age_index, self.feh_index, self.distance_index, self.AV_index = 3, 4, 5, 6
+        else:
+            raise ValueError("N must be 1, 2 or 3")
+        self.N = N
+
+        kwargs.pop("use_emcee", None)
+        self.kwargs = {}
+        for k, v in kwargs.items():
+            try:
+                val, unc = v
+                if not (np.isnan(val) or np.isnan(unc)):
+                    self.kwargs[k] = (np.float64(val), np.float64(unc))
+            except TypeError:
+                pass   # the reference logs "kwarg ignored" (starmodel.py:1431-1432)
+
+        self._bands = None
+        self._spec_props = None
+        self._props = None
+        self._param_names = None
+        self._compiled = None
+
+        self._priors = {"mass": ChabrierPrior(), "feh": FehPrior(), "age": AgePrior(),
+                        "distance": DistancePrior(), "AV": AVPrior()}
+        self._priors["eep"] = EEP_prior(self.ic, self._priors[self.ic.eep_replaces], bounds=eep_bounds)
+        self._bounds = {"mass": None, "feh": None, "age": None, "distance": DistancePrior().bounds,
+                        "AV": AVPrior().bounds, "eep": self._priors["eep"].bounds}
+        # Reset bounds to match IC bounds (starmodel.py:1458-1460)
+        for par in ["mass", "feh", "age"]:
+            self.bounds(par)
+        if maxAV is not None:
+            self.set_bounds(AV=(0, maxAV))
+        if max_distance is not None:
+            self.set_bounds(distance=(0, max_distance))
+        else:
+            if "parallax" in kwargs:
+                value, unc = kwargs["parallax"]
+                if value > 0:
+                    self.set_bounds(distance=(0, 1.0 / value * 2000))
+                elif value < 0:
+                    self.set_bounds(distance=(0, 1.0 / np.abs(unc) * 2000))
+        if halo_fraction is not None:
+            self._priors["feh"] = FehPrior(halo_fraction=halo_fraction)
+
+        self._directory = str(directory)
+        self._samples = None
+        self._derived_samples = None
+
+    # ---- reference attribute surface ---------------------------------------------------------------------
+    @property
+    def ic(self):
+        if type(self._ic) == type:
+            self._ic = self._ic()
+        return self._ic
+
+    @property
+    def labelstring(self):
+        return {1: "single", 2: "binary", 3: "triple"}[self.N]
+
+    @property
+    def param_names(self):
+        if self._param_names is None:
+            self._param_names = self.ic.param_names
+            if self.N == 2:
+                self._param_names = tuple(["eep_0", "eep_1"] + list(self.ic.param_names[1:]))
+            elif self.N == 3:
+                self._param_names = tuple(["eep_0", "eep_1", "eep_2"] + list(self.ic.param_names[1:]))
+        return self._param_names
+
+    @property
+    def bands(self):
+        if self._bands is None:
+            self._bands = [k for k in self.kwargs if k in self.ic.bc_grid.bands]
+        return self._bands
+
+    @property
+    def props(self):
+        if self._props is None:
+            self._props = [k for k in self.kwargs if k in self._not_a_band]
+        return self._props
+
+    @property
+    def spec_props(self):
+        if self._spec_props is None:
+            self._spec_props = [self.kwargs.get(k, (np.nan, np.nan)) for k in ["Teff", "logg", "feh"]]
+        return self._spec_props
+
+    @property
+    def n_params(self):
+        return len(self.param_names)
+
+    def bounds(self, prop):
+        if prop in ["eep_0", "eep_1", "eep_2"]:
+            prop = "eep"
+        if self._bounds[prop] is not None:
+            return self._bounds[prop]
+        elif prop in ("mass", "feh", "age"):
+            lo, hi = self.ic.model_grid.get_limits(prop)
+            self._bounds[prop] = (lo, hi)
+            self._priors[prop].bounds = (lo, hi)
+            self._compiled = None
+        else:
+            raise ValueError("Unknown property {}".format(prop))
+        return self._bounds[prop]
+
+    def set_bounds(self, **kwargs):
+        for k, v in kwargs.items():
+            if len(v) != 2:
+                raise ValueError("Must provide (min, max)")
+            self._bounds[k] = v
+            self._priors[k].bounds = v
+        self._compiled = None
+
+    def set_prior(self, **kwargs):
+        for prop, prior in kwargs.items():
+            self._priors[prop] = prior
+            self._bounds[prop] = prior.bounds
+        self._compiled = None
+
+    def prior(self, prop, val, **kwargs):
+        return self._priors[prop](val, **kwargs)
+
+    # ---- compilation to the device struct ------------------------------------------------------------------
+    def to_struct(self, band_columns=None):
+        """``iso_model`` image: observations (starmodel.py:1574-1580, 1599-1612) and the prior objects
+        (starmodel.py:1441-1448).  ``band_columns`` maps band name -> BC-pack column (catalog mode)."""
+        ic = self.ic
+        s = _lib.IsoModel()
+        s.n_stars = self.N
+        s.eep_replaces_age = 1 if ic.eep_replaces == "age" else 0
+        for i, v in enumerate(ic.param_index_order):
+            s.index_order[i] = int(v)
+        bands = list(self.bands)
+        if len(bands) > _lib.ISO_MAX_BANDS:
+            raise ValueError("at most %d bands per star model" % _lib.ISO_MAX_BANDS)
+        s.n_bands = len(bands)
+        for i, b in enumerate(bands):
+            s.band_col[i] = i if band_columns is None else band_columns[b]
+            s.mag_val[i], s.mag_unc[i] = [float(v) for v in self.kwargs[b]]
+        for i, (val, unc) in enumerate(self.spec_props):
+            s.spec_val[i], s.spec_unc[i] = float(val), float(unc)
+        for key, flag in (("parallax", "has_plax"), ("nu_max", "has_nu_max"), ("delta_nu", "has_delta_nu")):
+            setattr(s, flag, 1 if key in self.kwargs else 0)
+        s.plax, s.plax_unc = [float(v) for v in self.kwargs.get("parallax", (np.nan, np.nan))]
+        s.nu_max, s.nu_max_unc = [float(v) for v in self.kwargs.get("nu_max", (np.nan, np.nan))]
+        s.delta_nu, s.delta_nu_unc = [float(v) for v in self.kwargs.get("delta_nu", (np.nan, np.nan))]
+        if s.has_nu_max:
+            ci = ic.model_grid.interp.column_index
+            if "nu_max" not in ci or "delta_nu" not in ci:
+                raise KeyError("model grid has no nu_max / delta_nu columns")
+        eep = self._priors["eep"]
+        if not isinstance(eep, EEP_prior):
+            raise TypeError("the 'eep' prior must be an EEP_prior (it is evaluated inside the fused kernel)")
+        s.eep_has_bounds = 0 if eep._bounds is None else 1
+        if eep._bounds is not None:
+            s.eep_lo, s.eep_hi = float(eep._bounds[0]), float(eep._bounds[1])
+        s.eep_norm = float(eep._norm)
+        s.eep_orig = eep.orig_prior.to_struct()
+        for k in ("mass", "age", "feh", "distance", "AV"):
+            setattr(s, k, self._priors[k].to_struct())
+        return s
+
+    @property
+    def compiled(self):
+        if self._compiled is None:
+            self._compiled = CompiledModel(self.ic, [self.to_struct()], tuple(self.bands))
+        return self._compiled
+
+    # ---- the hot path ------------------------------------------------------------------------------------------
+    def _row(self, pars):
+        p = np.asarray(pars, dtype=np.float64).reshape(1, -1)
+        if p.shape[1] != self.n_params:
+            raise ValueError("expected %d parameters" % self.n_params)
+        return p
+
+    def lnpost_batch(self, pars, parts=False, out=None):
+        """Batched ``lnpost`` over rows of ``pars[N, n_params]`` — one fused kernel launch per chunk."""
+        return self.compiled.lnpost(pars, parts=parts, out=out)
+
+    def lnprior_batch(self, pars):
+        return self.compiled.lnpost(pars, parts=True)[1]
+
+    def lnlike_batch(self, pars):
+        return self.compiled.lnpost(pars, parts=True)[2]
+
+    def lnlike(self, pars):
+        return float(self.compiled.lnpost(self._row(pars), parts=True)[2][0])
+
+    def lnprior(self, pars):
+        return float(self.compiled.lnpost(self._row(pars), parts=True)[1][0])
+
+    def lnpost(self, p, **kwargs):
+        """``lnprior + lnlike`` with ``-inf`` when the prior is not finite (starmodel.py:538-542)."""
+        return float(self.compiled.lnpost(self._row(p))[0])
+
+    def mnest_prior(self, cube, ndim=None, nparams=None):
+        """Unit cube -> parameter box, in place (starmodel.py:1637-1640); ``cube`` may be ``[ndim]`` or ``[N, ndim]``."""
+        lo = np.array([self.bounds(par)[0] for par in self.param_names], dtype=np.float64)
+        hi = np.array([self.bounds(par)[1] for par in self.param_names], dtype=np.float64)
+        arr = np.asarray(cube)
+        direct = isinstance(cube, np.ndarray) and arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        work = arr if direct else np.ascontiguousarray([cube[i] for i in range(len(lo))], dtype=np.float64)
+        n = work.size // len(lo)
+        ctx = self.ic.ctx
+        ctx.check(_lib.lib().iso_mnest_prior(ctx.handle, _lib.dp(lo), _lib.dp(hi), len(lo), _lib.dp(work), n))
+        if not direct:      # e.g. the ctypes double* pymultinest hands over
+            for i in range(len(lo)):
+                cube[i] = work[i]
+
+    def mnest_loglike(self, cube, ndim=None, nparams=None):
+        n = self.n_params
+        return self.lnpost([cube[i] for i in range(n)])
+
+    def sample_from_prior(self, n, values=False, require_valid=True):
+        """Prior draws, re-drawn until ``lnpost`` is finite (starmodel.py:1716-1748); host RNG, batched validity check."""
+        import pandas as pd
+
+        if n == 0:
+            return pd.DataFrame(columns=self.param_names)
+        names = list(self.param_names)
+        cols = {}
+        for p in names:
+            if not p.startswith("eep"):
+                cols[p] = self._priors[p].sample(n)
+        for p in names:
+            if p.startswith("eep"):
+                if self.ic.eep_replaces == "age":
+                    cols[p] = self._priors["eep"].sample(n, mass=cols["mass"], feh=cols["feh"])
+                else:
+                    cols[p] = self._priors["eep"].sample(n, age=cols["age"], feh=cols["feh"])
+        if self.N > 1:      # keep the ordering the prior demands (starmodel.py:1618-1623)
+            e = np.sort(np.array([cols[p] for p in names[:self.N]]), axis=0)[::-1]
+            for k in range(self.N):
+                cols[names[k]] = e[k]
+        df = pd.DataFrame({p: np.asarray(cols[p], dtype=float) for p in names})
+        if require_valid:
+            bad = ~np.isfinite(self.lnpost_batch(df[names].values))
+            if bad.any():
+                new = self.sample_from_prior(int(bad.sum()), require_valid=True)
+                df.loc[bad, names] = new[names].values
+        return df[names].values if values else df
+
+
+class SingleStarModel(BasicStarModel):
+    def __init__(self, *args, **kwargs):
+        kwargs["N"] = 1
+        super().__init__(*args, **kwargs)
+
+
+class BinaryStarModel(BasicStarModel):
+    def __init__(self, *args, **kwargs):
+        kwargs["N"] = 2
+        super().__init__(*args, **kwargs)
+
+
+class TripleStarModel(BasicStarModel):
+    def __init__(self, *args, **kwargs):
+        kwargs["N"] = 3
+        super().__init__(*args, **kwargs)
+
+
+def compile_catalog(models):
+    """Catalog mode: compile many star models that share one interpolator into a single device
+    array; returns ``(CompiledModel, bands)`` where row ``i`` of a batch selects its model through ``model_of_row``."""
+    ic = models[0].ic
+    bands = []
+    for m in models:
+        if m.ic is not ic:
+            raise ValueError("catalog models must share one interpolator")
+        for b in m.bands:
+            if b not in bands:
+                bands.append(b)
+    col = {b: i for i, b in enumerate(bands)}
+    structs = [m.to_struct(band_columns=col) for m in models]
+    return CompiledModel(ic, structs, tuple(bands)), bands

@@ -98,3 +98,66 @@ def max_abs_err(a, b):
     if not m.any():
         return 0.0
     return float(np.max(np.abs(a[m] - b[m])))
+
+
+# ---------------------------------------------------------------------------
+# product-side builders (isochrones_b200 host objects from the golden specs)
+# ---------------------------------------------------------------------------
+
+def product_ic(kind, model, bc, eep_bounds=(0, 60), ctx=None):
+    import isochrones_b200 as ib
+
+    m = dict(model)
+    m.setdefault("limits", {"age": (5, 10.13), "feh": (-4, 0.5), "eep": tuple(eep_bounds), "mass": (0.1, 300)})
+    return ib.ichrone_from_arrays(kind, m, bc, eep_bounds=eep_bounds, ctx=ctx)
+
+
+def product_model_from_spec(spec, ic):
+    """Build the product's BasicStarModel exactly the way oracle/make_golden.py built the reference's."""
+    import isochrones_b200 as ib
+    from isochrones_b200 import priors as P
+
+    kwargs = {k: (v[0], v[1]) for k, v in spec["kwargs"].items()}
+    init_kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in spec["init_kwargs"].items()}
+    mod = ib.BasicStarModel(ic, N=spec["N"], **init_kw, **kwargs)
+    tweaks = spec["tweaks"]
+    if "set_bounds" in tweaks:
+        mod.set_bounds(**{k: tuple(v) for k, v in tweaks["set_bounds"].items()})
+    if "gauss_age" in tweaks:
+        mean, sig, b = tweaks["gauss_age"]
+        mod.set_prior(age=P.GaussianPrior(mean, sig, bounds=tuple(b)))
+    return mod
+
+
+def product_prior_cases():
+    """The prior objects of oracle/make_golden.py::golden_priors, built from the product's classes."""
+    from isochrones_b200 import priors as P
+
+    cases = {
+        "flat": P.FlatPrior((0.5, 2.5)),
+        "av": P.AVPrior(),
+        "flatlog": P.FlatLogPrior((6.0, 10.0)),
+        "age": P.AgePrior(),
+        "powerlaw": P.PowerLawPrior(-1.7, (0.2, 30.0)),
+        "distance": P.DistancePrior(),
+        "distance500": P.DistancePrior(max_distance=500),
+        "salpeter": P.SalpeterPrior(),
+        "q": P.QPrior(),
+        "gauss": P.GaussianPrior(9.6, 1.0),
+        "gauss_b": P.GaussianPrior(9.6, 1.0, bounds=(8, 10)),
+        "lognormal": P.LogNormalPrior(np.log(0.079), 0.69 * np.log(10)),
+        "feh": P.FehPrior(),
+        "feh_halo": P.FehPrior(halo_fraction=0.3),
+        "feh_nonlocal": P.FehPrior(local=False),
+        "chabrier": P.ChabrierPrior(),
+    }
+    fb = P.FehPrior()
+    fb.bounds = (-4, 0.5)
+    cases["feh_bounded"] = fb
+    cb = P.ChabrierPrior()
+    cb.bounds = (0.1, 300)
+    cases["chabrier_bounded"] = cb
+    ab = P.AgePrior()
+    ab.bounds = (5, 10.13)
+    cases["age_bounded"] = ab
+    return cases
