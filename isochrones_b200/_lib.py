@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libisochrones_b200.so")
+# ISO_B200_LIB selects another build of the same library (kernel tuning variants); never a different backend
+LIB_PATH = os.environ.get("ISO_B200_LIB") or os.path.join(HERE, "lib", "libisochrones_b200.so")
 
 ISO_MAX_BANDS = 16
 ISO_MAX_COMP = 3

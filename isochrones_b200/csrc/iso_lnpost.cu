@@ -16,6 +16,9 @@
 #include "iso_prior.cuh"
 
 #define ISO_LNPOST_THREADS 256
+#ifndef ISO_LNPOST_MIN_BLOCKS
+#define ISO_LNPOST_MIN_BLOCKS 2
+#endif
 
 // device image of one star model (built from the public iso_model by iso_models_stage)
 struct IsoGaussDev {
@@ -45,6 +48,7 @@ struct iso_models {
     int n_stars = 0;
     int device = 0;
     int max_col = -1;      // highest BC-pack column any model observes
+    IsoModelDev h_first;   // host copy of model 0 (passed by value in the kernel parameter block)
     bool needs_seismo = false;
 };
 
@@ -82,28 +86,39 @@ __device__ __forceinline__ bool iso_locate_smem(const IsoGridDev &g, const doubl
     return true;
 }
 
+// Everything the kernel reads besides the grids and the rows travels in the kernel parameter block (constant
+// bank): the grid descriptors, the buffer pointers and — outside catalog mode — the star model itself, so that
+// observation values and prior constants are constant-bank operands instead of memory loads.
+struct IsoLnpostParams {
+    IsoGridDev mg, bg;
+    IsoLnpostArgs a;
+    IsoModelDev model;   // the single model (unused in catalog mode)
+};
+
 template <int NSTARS, bool CATALOG>
-__global__ void __launch_bounds__(ISO_LNPOST_THREADS)
-iso_lnpost_kernel(const IsoGridDev mg, const IsoGridDev bg, const IsoLnpostArgs a)
+__global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : 1)
+iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 {
     constexpr int NDIMP = NSTARS + 4;
+    const IsoGridDev &mg = P.mg;
+    const IsoGridDev &bg = P.bg;
+    const IsoLnpostArgs &a = P.a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
-    IsoModelDev *s_model = reinterpret_cast<IsoModelDev *>(smem_raw + sizeof(double2) * a.smem_nodes);
 
-    // stage the axis tables (and, outside catalog mode, the star model) in shared memory
-    for (int g = 0; g < 2; g++) {
-        const IsoGridDev &gr = g == 0 ? mg : bg;
-        for (int d = 0; d < gr.ndim; d++) {
-            int so = a.smem_axis_off[g][d];
-            if (so < 0) continue;
-            for (int t = threadIdx.x; t < gr.ax[d].n; t += blockDim.x) s_nodes[so + t] = gr.nodes[gr.ax[d].off + t];
-        }
+    // stage the tables of the non-closed-form axes in shared memory (loops fully unrolled: the parameter block
+    // must only be indexed with compile-time constants or it is copied to local memory)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const int so = a.smem_axis_off[0][d];
+        if (so >= 0)
+            for (int t = threadIdx.x; t < mg.ax[d].n; t += blockDim.x) s_nodes[so + t] = mg.nodes[mg.ax[d].off + t];
     }
-    if (!CATALOG) {
-        const int *src = reinterpret_cast<const int *>(a.models);
-        int *dst = reinterpret_cast<int *>(s_model);
-        for (int t = threadIdx.x; t < (int)(sizeof(IsoModelDev) / sizeof(int)); t += blockDim.x) dst[t] = src[t];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int so = a.smem_axis_off[1][d];
+        if (so >= 0)
+            for (int t = threadIdx.x; t < bg.ax[d].n; t += blockDim.x) s_nodes[so + t] = bg.nodes[bg.ax[d].off + t];
     }
     __syncthreads();
 
@@ -113,7 +128,7 @@ iso_lnpost_kernel(const IsoGridDev mg, const IsoGridDev bg, const IsoLnpostArgs 
     const int bc_chunks = bg.ncols >> 2;
 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
-        const IsoModelDev &m = CATALOG ? a.models[a.model_of_row[i]] : *s_model;
+        const IsoModelDev &m = CATALOG ? a.models[a.model_of_row[i]] : P.model;
         double p[NDIMP];
 #pragma unroll
         for (int j = 0; j < NDIMP; j++) p[j] = a.pars[i * NDIMP + j];
@@ -344,7 +359,11 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
                          const int32_t *d_model_of_row, const double *d_pars, int64_t N, double *d_lnpost, double *d_lnprior,
                          double *d_lnlike)
 {
-    IsoLnpostArgs a;
+    IsoLnpostParams P;
+    P.mg = mp->dev;
+    P.bg = bp->dev;
+    P.model = models->h_first;
+    IsoLnpostArgs &a = P.a;
     a.models = models->d_models;
     a.model_of_row = d_model_of_row;
     a.pars = d_pars;
@@ -362,7 +381,7 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
             total += gr[g]->dev.ax[d].n;
         }
     a.smem_nodes = total;
-    size_t smem = sizeof(double2) * (size_t)total + sizeof(IsoModelDev);
+    size_t smem = sizeof(double2) * (size_t)(total > 0 ? total : 1);
     ISO_REQUIRE(ctx, smem <= 200 * 1024, "lnpost: axis tables do not fit in shared memory");
     const bool catalog = d_model_of_row != nullptr;
     int64_t want = (N + ISO_LNPOST_THREADS - 1) / ISO_LNPOST_THREADS;
@@ -374,7 +393,7 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
         if (smem > 48 * 1024)                                                                                             \
             ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                                (int)smem));                                                               \
-        iso_lnpost_kernel<NS, CAT><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(mp->dev, bp->dev, a);                        \
+        iso_lnpost_kernel<NS, CAT><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                        \
     } while (0)
     switch (models->n_stars * 2 + (catalog ? 1 : 0)) {
     case 2: ISO_LAUNCH(1, false); break;
@@ -471,6 +490,7 @@ int iso_models_stage(iso_ctx *ctx, const iso_model *h_models, int n_models, iso_
     m->device = ctx->device;
     m->max_col = max_col;
     m->needs_seismo = seismo;
+    m->h_first = dev[0];
     cudaError_t e = cudaMalloc(&m->d_models, sizeof(IsoModelDev) * (size_t)n_models);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->d_models, dev.data(), sizeof(IsoModelDev) * (size_t)n_models, cudaMemcpyHostToDevice, ctx->stream);

@@ -20,9 +20,12 @@ static inline void iso_prior_leaf_fill(iso_prior_leaf *p)
 {
     p->k[0] = p->k[1] = 0.0;
     switch (p->kind) {
-    case ISO_PRIOR_FLAT:  // priors.py:287-289
+    case ISO_PRIOR_FLAT: {  // priors.py:287-289; lnpdf is the constant log(pdf / _norm) (or -inf when that is 0)
         p->k[0] = 1.0 / (p->hi - p->lo);
+        double pdf = p->k[0] / p->norm;
+        p->k[1] = pdf == 0.0 ? -INFINITY : log(pdf);
         break;
+    }
     case ISO_PRIOR_FLATLOG:  // priors.py:300-302
         p->k[0] = log(10.0);
         p->k[1] = pow(10.0, p->hi) - pow(10.0, p->lo);
@@ -164,6 +167,7 @@ __device__ __forceinline__ double iso_leaf_lnpdf(const iso_prior_leaf &p, double
     if (p.flags & ISO_PF_BOUNDED) {
         if ((p.flags & ISO_PF_HAS_BOUNDS) && iso_outside(x, p.lo, p.hi)) return iso_neg_inf();
         if (iso_kind_has_lnpdf(p.kind)) return iso_leaf_lnpdf_raw(p, x);
+        if (p.kind == ISO_PRIOR_FLAT) return p.k[1];   // x-independent: log evaluated once at staging time
         return iso_log_or_neginf(iso_leaf_pdf(p, x));
     }
     if (iso_kind_has_lnpdf(p.kind)) return iso_leaf_lnpdf_raw(p, x);

@@ -1,0 +1,127 @@
+"""Multi-GPU partitioning of the lnpost path: one process per GPU, grids replicated, the rows of a
+batch (walkers / live points / per-star chains) sharded in contiguous blocks.  There is no data-path collective;
+the only exchange is the all-gather of per-row results that a sampler's acceptance step needs.
+
+The reference has no counterpart: its batch recipes are process pools over stars (``notebooks/batch-demo.ipynb``)
+and MultiNest's own MPI (``starmodel.py:755-797``).
+
+``RowSharder`` is pure host logic (tested with gloo, world_size 2, on CPU); ``NcclGather`` binds the library's
+``ncclAllGather`` entry point on device buffers.  The 128-byte NCCL unique id travels through any byte-broadcast
+the launcher offers (``torch_exchange`` for torchrun, ``file_exchange`` for a shared directory).
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+
+
+class RowSharder(object):
+    """Contiguous, balanced row blocks: rank r owns rows [start(r), stop(r)); the first ``n % world`` ranks hold one
+    extra row.  Gathers are padded to ``pad`` rows per rank so that one fixed-size all-gather serves every rank."""
+
+    def __init__(self, n_rows, world, rank=0):
+        if world < 1 or not (0 <= rank < world) or n_rows < 0:
+            raise ValueError("bad sharding arguments")
+        self.n, self.world, self.rank = int(n_rows), int(world), int(rank)
+        base, extra = divmod(self.n, self.world)
+        self.counts = [base + (1 if r < extra else 0) for r in range(self.world)]
+        self.starts = [sum(self.counts[:r]) for r in range(self.world)]
+        self.pad = max(self.counts) if self.counts else 0
+
+    def bounds(self, rank=None):
+        r = self.rank if rank is None else rank
+        return self.starts[r], self.starts[r] + self.counts[r]
+
+    def local(self, rows, rank=None):
+        a, b = self.bounds(rank)
+        return rows[a:b]
+
+    def padded(self, local_values, fill=np.nan):
+        """This rank's results padded to ``pad`` entries (send buffer of the all-gather)."""
+        out = np.full((self.pad,) + tuple(np.shape(local_values)[1:]), fill, dtype=np.float64)
+        out[:len(local_values)] = local_values
+        return out
+
+    def assemble(self, gathered):
+        """``gathered[world, pad, ...]`` (rank-major output of the all-gather) -> ``[n, ...]`` in row order."""
+        g = np.asarray(gathered)
+        if g.shape[:2] != (self.world, self.pad):
+            raise ValueError("gathered must be [world=%d, pad=%d, ...], got %r" % (self.world, self.pad, g.shape))
+        return np.concatenate([g[r, :self.counts[r]] for r in range(self.world)], axis=0)
+
+
+def torch_exchange(dist):
+    """Byte broadcast from rank 0 over an initialised ``torch.distributed`` group (plumbing only)."""
+    def exchange(payload):
+        obj = [payload]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    return exchange
+
+
+def file_exchange(path, rank, timeout=120.0):
+    """Byte broadcast from rank 0 through a file visible to every rank (no torch needed)."""
+    def exchange(payload):
+        if rank == 0:
+            tmp = path + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(payload)
+            os.replace(tmp, path)
+            return payload
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > timeout:
+                raise TimeoutError("no NCCL id at %s" % path)
+            time.sleep(0.01)
+        with open(path, "rb") as f:
+            return f.read()
+    return exchange
+
+
+class NcclGather(object):
+    """All-gather of float64 device buffers across the ranks' contexts (``iso_nccl_init`` / ``iso_allgather_f64``)."""
+
+    def __init__(self, ctx, rank, world, exchange):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            ctx.check(_lib.lib().iso_nccl_unique_id(buf))
+        payload = exchange(bytes(buf.raw) if rank == 0 else None)
+        ident = C.create_string_buffer(payload, 128)
+        ctx.check(_lib.lib().iso_nccl_init(ctx.handle, ident, rank, world))
+
+    def allgather(self, d_send, n, d_recv):
+        """``d_recv[world * n] <- concat_r d_send_r[n]``; asynchronous on the context's compute stream."""
+        self.ctx.check(_lib.lib().iso_allgather_f64(self.ctx.handle, d_send, int(n), d_recv))
+
+    def close(self):
+        _lib.lib().iso_nccl_destroy(self.ctx.handle)
+
+
+def sharded_lnpost(compiled, pars, sharder, gather):
+    """Evaluate this rank's block of ``pars[N, ndim]`` and all-gather the results: every rank returns ``lnpost[N]``.
+
+    ``gather(send[pad]) -> [world, pad]`` is the collective (NCCL through ``device_gather`` below on GPUs; a gloo
+    all-gather in the CPU tests of the host logic)."""
+    local = compiled.lnpost(np.ascontiguousarray(sharder.local(pars)))
+    return sharder.assemble(gather(sharder.padded(local)))
+
+
+def device_gather(ctx, comm, world):
+    """Host-array front end of ``NcclGather`` (stages through device buffers; for sampler-sized batches)."""
+    def gather(send):
+        n = len(send)
+        d_s, d_r = ctx.dev_alloc(n * 8), ctx.dev_alloc(world * n * 8)
+        try:
+            ctx.h2d(d_s, send)
+            comm.allgather(d_s, n, d_r)
+            out = np.empty((world, n))
+            ctx.d2h(out, d_r)
+        finally:
+            ctx.dev_free(d_s)
+            ctx.dev_free(d_r)
+        return out
+    return gather

@@ -58,6 +58,13 @@ class CompiledModel(object):
             return lnpost, lnprior, lnlike
         return lnpost
 
+    def lnpost_device(self, d_pars, n, d_lnpost, d_lnprior=None, d_lnlike=None, d_model_of_row=None):
+        """Asynchronous launch on device-resident buffers (``iso_lnpost_batch_device``): ``d_*`` are device
+        pointers from ``Context.dev_alloc``; the call returns as soon as the kernel is queued."""
+        self.ctx.check(_lib.lib().iso_lnpost_batch_device(
+            self.ctx.handle, self.model_pack.handle, self.bc_pack.handle, self.handle, d_model_of_row, d_pars, int(n),
+            d_lnpost, d_lnprior, d_lnlike))
+
     def close(self):
         if self.handle:
             _lib.lib().iso_models_destroy(self.ctx.handle, self.handle)
