@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISO_ABI_VERSION 1
+#define ISO_ABI_VERSION 2
 
 #define ISO_OK 0
 #define ISO_E_INVALID (-1) /* bad argument */
@@ -126,10 +126,9 @@ typedef struct {
     /* GAUSSIAN mean, sigma, norm, lognorm | LOGNORMAL mu, sigma, scale, log_s | POWERLAW alpha |
        FEH halo_fraction */
     double a[4];
-    /* derived constants, filled in by the library when the struct is staged (callers leave them 0):
-       FLAT 1/(hi-lo) | FLATLOG ln10, 10^hi-10^lo | POWERLAW C, ln C | GAUSSIAN ln sqrt(2 pi), ln sigma |
-       LOGNORMAL ln(1/sqrt(2 pi)), 1/sqrt(2 pi) */
-    double k[2];
+    /* derived constants (reciprocals, logs, prefactors), filled in by the library when the struct is staged;
+       callers leave them 0 */
+    double k[4];
 } iso_prior_leaf;
 
 typedef struct {
@@ -139,6 +138,8 @@ typedef struct {
     double breakpoints[ISO_MAX_COMP - 1];
     double norms[ISO_MAX_COMP];
     double lognorms[ISO_MAX_COMP];
+    double inv_norms[ISO_MAX_COMP]; /* derived, filled in by the library */
+    double inv_norm;                /* derived, filled in by the library */
     iso_prior_leaf comp[ISO_MAX_COMP];
 } iso_prior;
 

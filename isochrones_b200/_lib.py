@@ -36,13 +36,14 @@ class IsoError(RuntimeError):
 
 class IsoPriorLeaf(C.Structure):
     _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
-                ("norm", C.c_double), ("a", C.c_double * 4), ("k", C.c_double * 2)]
+                ("norm", C.c_double), ("a", C.c_double * 4), ("k", C.c_double * 4)]
 
 
 class IsoPrior(C.Structure):
     _fields_ = [("self", IsoPriorLeaf), ("n_comp", C.c_int32), ("pad_", C.c_int32),
                 ("breakpoints", C.c_double * (ISO_MAX_COMP - 1)), ("norms", C.c_double * ISO_MAX_COMP),
-                ("lognorms", C.c_double * ISO_MAX_COMP), ("comp", IsoPriorLeaf * ISO_MAX_COMP)]
+                ("lognorms", C.c_double * ISO_MAX_COMP), ("inv_norms", C.c_double * ISO_MAX_COMP),
+                ("inv_norm", C.c_double), ("comp", IsoPriorLeaf * ISO_MAX_COMP)]
 
 
 class IsoModel(C.Structure):

@@ -38,8 +38,10 @@ struct IsoModelDev {
     IsoGaussDev spec[3];
     IsoGaussDev mag[ISO_MAX_BANDS];   // indexed by BC-pack column
     IsoGaussDev plax, nu_max, delta_nu;
-    double eep_lo, eep_hi, eep_norm;
+    double eep_lo, eep_hi, eep_norm, eep_inv_norm;
     iso_prior eep_orig, mass, age, feh, distance, AV;
+    int profile_default;   // 1: the priors match ISO_PROFILE_DEFAULT
+    int pad2_;
 };
 
 struct iso_models {
@@ -50,6 +52,8 @@ struct iso_models {
     int max_col = -1;      // highest BC-pack column any model observes
     IsoModelDev h_first;   // host copy of model 0 (passed by value in the kernel parameter block)
     bool needs_seismo = false;
+    bool profile_default = false;   // every model matches ISO_PROFILE_DEFAULT
+    bool track = false;             // evolution-track grid (all models share the grid kind)
 };
 
 struct IsoLnpostArgs {
@@ -95,10 +99,19 @@ struct IsoLnpostParams {
     IsoModelDev model;   // the single model (unused in catalog mode)
 };
 
-template <int NSTARS, bool CATALOG>
+// PROFILE selects how the priors are evaluated:
+//   ISO_PROFILE_DEFAULT — the prior classes of a default BasicStarModel (starmodel.py:1441-1448): Chabrier mass
+//       (BrokenPrior[LogNormal, PowerLaw]), FehPrior, FlatLog age, PowerLaw distance, Flat AV, with any bounds /
+//       constants; the kinds are compile-time, so the code is small, switch-free and shares log(distance);
+//   ISO_PROFILE_GENERIC — any supported prior object per parameter (set_prior), through out-of-line dispatchers.
+// TRACK: evolution-track grid (mass, eep, feh, d, AV) vs isochrone grid (eep_0.., age, feh, d, AV).
+enum { ISO_PROFILE_GENERIC = 0, ISO_PROFILE_DEFAULT = 1 };
+
+template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK>
 __global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : 1)
 iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 {
+    constexpr bool DEF = PROFILE == ISO_PROFILE_DEFAULT;
     constexpr int NDIMP = NSTARS + 4;
     const IsoGridDev &mg = P.mg;
     const IsoGridDev &bg = P.bg;
@@ -140,10 +153,20 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
         if (NSTARS == 3) order_bad = !(p[0] > p[1]) && (p[1] > p[2]);
         // track grids (mass, eep, feh, ..): p[0] is the mass (prior "mass") and `other` the EEP;
         // isochrone grids (eep_0.., age, feh, ..): p[k] are the EEPs and `other` the age (prior "age")
-        const double lnp_other = m.eep_replaces_age ? iso_prior_lnpdf(m.mass, p[0]) : iso_prior_lnpdf(m.age, other);
-        const double lnp_feh = iso_prior_lnpdf(m.feh, feh_in);
-        const double lnp_dist = iso_prior_lnpdf(m.distance, dist);
-        const double lnp_AV = iso_prior_lnpdf(m.AV, AV);
+        double lnp_other, lnp_feh, lnp_dist, lnp_AV, lnd = 0.0;
+        if (DEF) {
+            lnp_other = TRACK ? iso_broken2_lnpdf<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.mass, p[0])
+                              : iso_leaf_lnpdf<ISO_PRIOR_FLATLOG>(m.age.self, other);
+            lnp_feh = iso_leaf_lnpdf<ISO_PRIOR_FEH>(m.feh.self, feh_in);
+            lnd = log(dist);   // shared by the distance prior and the distance modulus
+            lnp_dist = iso_leaf_lnpdf<ISO_PRIOR_POWERLAW, true>(m.distance.self, dist, lnd);
+            lnp_AV = iso_leaf_lnpdf<ISO_PRIOR_FLAT>(m.AV.self, AV);
+        } else {
+            lnp_other = TRACK ? iso_prior_lnpdf_dyn(&m.mass, p[0]) : iso_prior_lnpdf_dyn(&m.age, other);
+            lnp_feh = iso_prior_lnpdf_dyn(&m.feh, feh_in);
+            lnp_dist = iso_prior_lnpdf_dyn(&m.distance, dist);
+            lnp_AV = iso_prior_lnpdf_dyn(&m.AV, AV);
+        }
         const double cheap = lnp_other + lnp_feh + lnp_dist + lnp_AV;
         if (!want_parts && (order_bad || !isfinite(cheap))) {
             // lnprior is already known to be -inf or NaN: StarModel.lnpost returns -inf (starmodel.py:540-541)
@@ -159,8 +182,9 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 #pragma unroll
         for (int k = 0; k < NSTARS; k++) {
             // star k uses [pars[k], shared parameters...]  (likelihood.py:43-54)
-            const double sp[5] = {p[k], other, feh_in, dist, AV};
-            const double x[3] = {iso_sel5(sp, m.index_order[0]), iso_sel5(sp, m.index_order[1]), iso_sel5(sp, m.index_order[2])};
+            // model-grid coordinates pars[index_order[0..2]] (models.py:669, 696): tracks (feh, mass, eep), isochrones
+            // (age, feh, eep) — fixed by the grid kind, checked on the host
+            const double x[3] = {TRACK ? feh_in : other, TRACK ? p[0] : feh_in, TRACK ? other : p[k]};
             double y[3];
             int idx[3];
             double v[8] = {nan, nan, nan, nan, nan, nan, nan, nan};
@@ -185,12 +209,23 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
                 }
             }
             // EEP_prior.lnpdf: BoundedPrior.lnpdf :131-140 -> Prior.pdf :54-59 -> EEP_prior._pdf :423-429
-            const double eep = m.eep_replaces_age ? other : p[k];
+            const double eep = TRACK ? other : p[k];
             if (m.eep_has_bounds && iso_outside(eep, m.eep_lo, m.eep_hi)) {
                 lnp_eep[k] = neg_inf;
+            } else if (DEF && TRACK) {
+                // orig_prior = FlatLogPrior on log10 age: pdf = k2 10^age inside its bounds, so
+                // log(pdf * deriv / norm) = age ln10 + log(k2 deriv / norm); 0 -> -inf, negative / NaN -> NaN as in
+                // `np.log(pdf) if pdf else -np.inf`
+                const iso_prior_leaf &op = m.eep_orig.self;
+                const double age = v[ISO_MP_ORIG];
+                if ((op.flags & ISO_PF_HAS_BOUNDS) && iso_outside(age, op.lo, op.hi))
+                    lnp_eep[k] = neg_inf;
+                else
+                    lnp_eep[k] = fma(age, op.k[0], iso_log_or_neginf(op.k[2] * v[ISO_MP_DERIV] * m.eep_inv_norm));
             } else {
-                double pdf = iso_prior_call(m.eep_orig, v[ISO_MP_ORIG]) * v[ISO_MP_DERIV];
-                lnp_eep[k] = iso_log_or_neginf(pdf / m.eep_norm);
+                double pdf = DEF ? iso_broken2_call<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.eep_orig, v[ISO_MP_ORIG])
+                                 : iso_prior_call_dyn(&m.eep_orig, v[ISO_MP_ORIG]);
+                lnp_eep[k] = iso_log_or_neginf(pdf * v[ISO_MP_DERIV] * m.eep_inv_norm);
             }
             Mbol[k] = v[ISO_MP_MBOL];
             if (k == 0) {   // companions' Teff / logg / feh are discarded (likelihood.py:76, 96)
@@ -211,7 +246,7 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
             lnprior = neg_inf;
         } else {
             lnprior = 0.0;
-            if (m.eep_replaces_age) {   // (mass, eep, feh, distance, AV)
+            if (TRACK) {   // (mass, eep, feh, distance, AV)
                 lnprior += lnp_other;
                 lnprior += lnp_eep[0];
             } else {                    // (eep_0 .. eep_{N-1}, age, feh, distance, AV)
@@ -236,7 +271,8 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
         if (m.spec_mask & 2) ll += iso_gauss(m.spec[1], logg);
         if (m.spec_mask & 4) ll += iso_gauss(m.spec[2], feh_s);
         if (m.obs_mask) {
-            const double dist_mod = 5.0 * log10(dist / 10.0);   // mags.py:52
+            // mags.py:52: 5 log10(d / 10); the default profile already holds log(d)
+            const double dist_mod = DEF ? 5.0 * fma(lnd, 0.43429448190325182765, -1.0) : 5.0 * log10(dist / 10.0);
             for (int ch = 0; ch < bc_chunks; ch++) {
                 const int cm = (m.obs_mask >> (4 * ch)) & 0xF;
                 if (!cm) continue;
@@ -317,6 +353,16 @@ static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
         d.index_order[j] = s.index_order[j];
     }
     ISO_REQUIRE(ctx, seen == 31, "iso_model: index_order is not a permutation");
+    {   // the two orders the reference defines (models.py:669, 696); the kernel hard-wires them per grid kind
+        static const int track_order[5] = {2, 0, 1, 3, 4}, iso_order[5] = {1, 2, 0, 3, 4};
+        const int *want = d.eep_replaces_age ? track_order : iso_order;
+        for (int j = 0; j < 5; j++)
+            if (d.index_order[j] != want[j])
+                return iso_set_error(ctx, ISO_E_UNSUPPORTED, "iso_model: index_order must be (2,0,1,3,4) for track grids and "
+                                                             "(1,2,0,3,4) for isochrone grids");
+    }
+    ISO_REQUIRE(ctx, !(d.eep_replaces_age && d.n_stars > 1),
+                "iso_model: multiple stars need an isochrone grid (starmodel.py:1396-1397)");
     for (int i = 0; i < 3; i++) {
         d.spec[i] = make_gauss(s.spec_val[i], s.spec_unc[i]);
         if (s.spec_val[i] == s.spec_val[i]) d.spec_mask |= 1 << i;
@@ -337,6 +383,7 @@ static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
     d.eep_lo = s.eep_lo;
     d.eep_hi = s.eep_hi;
     d.eep_norm = s.eep_norm;
+    d.eep_inv_norm = 1.0 / s.eep_norm;
     d.eep_has_bounds = s.eep_has_bounds ? 1 : 0;
     const iso_prior *src[6] = {&s.eep_orig, &s.mass, &s.age, &s.feh, &s.distance, &s.AV};
     iso_prior *dst[6] = {&d.eep_orig, &d.mass, &d.age, &d.feh, &d.distance, &d.AV};
@@ -352,6 +399,15 @@ static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
         ISO_REQUIRE(ctx, iso_prior_valid(*src[i]), "iso_model: unsupported prior kind (no CPU fallback exists)");
         iso_prior_fill(dst[i]);
     }
+    // the default BasicStarModel prior classes (any bounds / constants) -> the specialised kernel profile
+    const iso_prior &other = d.eep_replaces_age ? d.mass : d.age;
+    bool def = d.feh.self.kind == ISO_PRIOR_FEH && d.distance.self.kind == ISO_PRIOR_POWERLAW &&
+               d.AV.self.kind == ISO_PRIOR_FLAT && (d.AV.self.flags & ISO_PF_BOUNDED);
+    if (d.eep_replaces_age)
+        def = def && iso_prior_is_chabrier_like(other) && d.eep_orig.self.kind == ISO_PRIOR_FLATLOG;
+    else
+        def = def && other.self.kind == ISO_PRIOR_FLATLOG && iso_prior_is_chabrier_like(d.eep_orig);
+    d.profile_default = def ? 1 : 0;
     return ISO_OK;
 }
 
@@ -388,23 +444,36 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-#define ISO_LAUNCH(NS, CAT)                                                                                               \
-    do {                                                                                                                  \
-        if (smem > 48 * 1024)                                                                                             \
-            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                               (int)smem));                                                               \
-        iso_lnpost_kernel<NS, CAT><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                        \
+#define ISO_LAUNCH4(NS, CAT, PROF, TRK)                                                                                  \
+    do {                                                                                                                 \
+        if (smem > 48 * 1024)                                                                                            \
+            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT, PROF, TRK>,                                    \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        iso_lnpost_kernel<NS, CAT, PROF, TRK><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                              \
     } while (0)
-    switch (models->n_stars * 2 + (catalog ? 1 : 0)) {
-    case 2: ISO_LAUNCH(1, false); break;
-    case 3: ISO_LAUNCH(1, true); break;
-    case 4: ISO_LAUNCH(2, false); break;
-    case 5: ISO_LAUNCH(2, true); break;
-    case 6: ISO_LAUNCH(3, false); break;
-    case 7: ISO_LAUNCH(3, true); break;
+#define ISO_LAUNCH2(NS, TRK)                                                           \
+    do {                                                                               \
+        if (catalog) {                                                                 \
+            if (def) ISO_LAUNCH4(NS, true, ISO_PROFILE_DEFAULT, TRK);                  \
+            else ISO_LAUNCH4(NS, true, ISO_PROFILE_GENERIC, TRK);                      \
+        } else {                                                                       \
+            if (def) ISO_LAUNCH4(NS, false, ISO_PROFILE_DEFAULT, TRK);                 \
+            else ISO_LAUNCH4(NS, false, ISO_PROFILE_GENERIC, TRK);                     \
+        }                                                                              \
+    } while (0)
+    const bool def = models->profile_default;
+    const bool track = models->track;
+    switch (models->n_stars) {
+    case 1:
+        if (track) ISO_LAUNCH2(1, true);
+        else ISO_LAUNCH2(1, false);
+        break;
+    case 2: ISO_LAUNCH2(2, false); break;
+    case 3: ISO_LAUNCH2(3, false); break;
     default: return iso_set_error(ctx, ISO_E_INVALID, "lnpost: bad n_stars");
     }
-#undef ISO_LAUNCH
+#undef ISO_LAUNCH2
+#undef ISO_LAUNCH4
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());
     return ISO_OK;
@@ -474,11 +543,13 @@ int iso_models_stage(iso_ctx *ctx, const iso_model *h_models, int n_models, iso_
     *out = nullptr;
     std::vector<IsoModelDev> dev((size_t)n_models);
     int max_col = -1;
-    bool seismo = false;
+    bool seismo = false, all_default = true;
     for (int i = 0; i < n_models; i++) {
         int rc = convert_model(ctx, h_models[i], dev[i]);
         if (rc != ISO_OK) return rc;
         ISO_REQUIRE(ctx, dev[i].n_stars == dev[0].n_stars, "iso_models_stage: all models must share n_stars");
+        ISO_REQUIRE(ctx, dev[i].eep_replaces_age == dev[0].eep_replaces_age, "iso_models_stage: all models must share the grid kind");
+        all_default = all_default && dev[i].profile_default;
         for (int c = 0; c < ISO_MAX_BANDS; c++)
             if (dev[i].obs_mask & (1 << c)) max_col = c > max_col ? c : max_col;
         seismo = seismo || dev[i].has_nu_max;
@@ -491,6 +562,8 @@ int iso_models_stage(iso_ctx *ctx, const iso_model *h_models, int n_models, iso_
     m->max_col = max_col;
     m->needs_seismo = seismo;
     m->h_first = dev[0];
+    m->profile_default = all_default;
+    m->track = dev[0].eep_replaces_age != 0;
     cudaError_t e = cudaMalloc(&m->d_models, sizeof(IsoModelDev) * (size_t)n_models);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->d_models, dev.data(), sizeof(IsoModelDev) * (size_t)n_models, cudaMemcpyHostToDevice, ctx->stream);

@@ -13,7 +13,7 @@ __global__ void iso_prior_eval_kernel(const iso_prior *__restrict__ prior, int w
     }
     __syncthreads();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
-        out[i] = which == 0 ? iso_prior_lnpdf(p, x[i]) : iso_prior_call(p, x[i]);
+        out[i] = which == 0 ? iso_prior_lnpdf_dyn(&p, x[i]) : iso_prior_call_dyn(&p, x[i]);
 }
 
 struct PriorUser {

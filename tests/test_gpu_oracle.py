@@ -225,3 +225,28 @@ def test_catalog_mode(world):
         # same rows through the single-model launch: the band terms are summed in the model's own band order there
         # and in catalog-pack column order here, so agreement is to rounding, not bit for bit
         _compare(models[s].lnpost_batch(pars[sel]), got[sel], 1e-9)
+
+
+@pytest.mark.parametrize("kind,N", [("track", 1), ("iso", 2)])
+def test_custom_priors_generic_profile(world, kind, N):
+    """set_prior with non-default classes routes the launch to the generic-prior kernel profile; results must still
+    match the oracle (GaussianPrior on feh, bounded GaussianPrior on distance, LogNormal-free Salpeter-like mass)."""
+    from isochrones_b200 import priors as P
+
+    mod, _, truth = _model(world, kind, N)
+    mod.set_prior(feh=P.GaussianPrior(-0.1, 0.3, bounds=(-2.0, 0.5)), AV=P.FlatPrior((0.0, 0.8)),
+                  distance=P.GaussianPrior(100.0, 30.0, bounds=(1.0, 400.0)))
+    if kind == "track":
+        mod.set_prior(mass=P.SalpeterPrior(bounds=(0.2, 20.0)))
+    else:
+        mod.set_prior(age=P.GaussianPrior(9.6, 0.5, bounds=(8.0, 10.1)))
+    from oracle import oracle
+
+    om = oracle.StarModel(mod, model_grid=world["og_" + kind], bc_grid=world["og_bc"])
+    pars = _batches(kind, mod, truth, world["trk" if kind == "track" else "iso"]["axes"], 30_000)
+    got = mod.lnpost_batch(pars, parts=True)
+    want = om.lnpost_batch(pars, n_threads=8, parts=True)
+    _compare(got[1], want[1], 1e-9)
+    _compare(got[2], want[2], ATOL_LNPOST)
+    _compare(got[0], want[0], ATOL_LNPOST)
+    assert np.isfinite(want[0]).sum() > 10_000
