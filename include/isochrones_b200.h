@@ -206,12 +206,17 @@ int iso_mnest_prior(iso_ctx *ctx, const double *h_lo, const double *h_hi, int nd
  * on-device ensemble sampler (the emcee stretch move the reference drives through
  * emcee.EnsembleSampler(nwalkers, npars, mod.lnpost), starmodel.py:966) — SURVEY.md §8f-1
  * ---------------------------------------------------------------------------------------------- */
+/* One persistent CTA per chain, one thread per walker of the active half (n_walkers even, <= 1024); the initial
+ * lnpost of h_p0 is evaluated at creation.  `models` holds one model (every chain samples it) or n_chains models
+ * (catalog mode: chain c samples star c).  Randomness is Philox4x32-10 keyed by `seed`. */
 int iso_sampler_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
                        int n_chains, int n_walkers, const double *h_p0 /* [n_chains, n_walkers, ndim] */,
                        uint64_t seed, double stretch_a, iso_sampler **out);
-/* Run n_steps full ensemble steps.  h_chain ([n_steps / thin, n_chains, n_walkers, ndim]) and
+/* Run n_steps full ensemble steps in ONE kernel launch.  h_chain ([n_steps / thin, n_chains, n_walkers, ndim]) and
  * h_lnprob ([n_steps / thin, n_chains, n_walkers]) may be NULL. */
 int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double *h_chain, double *h_lnprob);
+/* Current ensemble (h_pos [n_chains, n_walkers, ndim], h_lnprob [n_chains, n_walkers]; either may be NULL),
+ * accepted proposals per chain (n_accepted[n_chains], may be NULL) and proposals made so far per chain. */
 int iso_sampler_state(iso_ctx *ctx, iso_sampler *s, double *h_pos, double *h_lnprob, int64_t *n_accepted,
                       int64_t *n_proposed);
 int iso_sampler_destroy(iso_ctx *ctx, iso_sampler *s);

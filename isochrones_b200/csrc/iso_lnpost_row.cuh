@@ -1,0 +1,319 @@
+// isochrones_b200 — evaluation of ONE row of the lnpost path (device function shared by the batch kernel in
+// iso_lnpost.cu and the on-device ensemble sampler in iso_sampler.cu).
+//
+// Per row it replaces the chain
+//   StarModel.lnpost            starmodel.py:538-542
+//   BasicStarModel.lnprior      starmodel.py:1616-1635   (+ the prior classes, iso_prior.cuh; EEP_prior priors.py:409-429)
+//   BasicStarModel.lnlike       starmodel.py:1563-1614
+//   star_lnlike                 likelihood.py:16-147     (gauss_lnprob :10-13, fast_addmags utils.py:67-75)
+//   interp_mag                  mags.py:8-61             (interp_value_3d / _4d interp.py:252-338)
+#pragma once
+
+#include "iso_common.cuh"
+#include "iso_prior.cuh"
+
+// device image of one star model (built from the public iso_model by iso_models_stage)
+struct IsoGaussDev {
+    double val;   // observed value
+    double c;     // log(1 / sqrt(2 pi)) + log(unc)      (likelihood.py:13 — note the PLUS sign)
+    double h;     // 1 / (unc * unc)
+};
+
+struct IsoModelDev {
+    int n_stars, eep_replaces_age;
+    int index_order[5];
+    int obs_mask;          // bit c: BC-pack column c is an observed band
+    int spec_mask;         // bit i: Teff / logg / feh observed (value not NaN, likelihood.py:127)
+    int has_plax, has_nu_max, has_delta_nu;
+    int eep_has_bounds;
+    int pad_;
+    IsoGaussDev spec[3];
+    IsoGaussDev mag[ISO_MAX_BANDS];   // indexed by BC-pack column
+    IsoGaussDev plax, nu_max, delta_nu;
+    double eep_lo, eep_hi, eep_norm, eep_inv_norm;
+    iso_prior eep_orig, mass, age, feh, distance, AV;
+    int profile_default;   // 1: the priors match ISO_PROFILE_DEFAULT
+    int pad2_;
+};
+
+struct iso_models {
+    IsoModelDev *d_models = nullptr;
+    int n_models = 0;
+    int n_stars = 0;
+    int device = 0;
+    int max_col = -1;      // highest BC-pack column any model observes
+    IsoModelDev h_first;   // host copy of model 0 (passed by value in the kernel parameter block)
+    bool needs_seismo = false;
+    bool profile_default = false;   // every model matches ISO_PROFILE_DEFAULT
+    bool track = false;             // evolution-track grid (all models share the grid kind)
+};
+
+// PROFILE selects how the priors are evaluated:
+//   ISO_PROFILE_DEFAULT — the prior classes of a default BasicStarModel (starmodel.py:1441-1448): Chabrier mass
+//       (BrokenPrior[LogNormal, PowerLaw]), FehPrior, FlatLog age, PowerLaw distance, Flat AV, with any bounds /
+//       constants; the kinds are compile-time, so the code is small, switch-free and shares log(distance);
+//   ISO_PROFILE_GENERIC — any supported prior object per parameter (set_prior), through out-of-line dispatchers.
+// TRACK: evolution-track grid (mass, eep, feh, d, AV) vs isochrone grid (eep_0.., age, feh, d, AV).
+enum { ISO_PROFILE_GENERIC = 0, ISO_PROFILE_DEFAULT = 1 };
+
+// the grids as a kernel sees them: descriptors (kernel parameter block) + axis tables staged in shared memory
+struct IsoRowGrids {
+    IsoGridDev mg, bg;
+    int smem_axis_off[2][ISO_MAX_DIM];   // offset (in double2) of each axis table in shared memory; -1: closed form
+    int smem_nodes;                      // double2 entries of axis tables in shared memory
+};
+
+struct IsoRowResult {
+    double lnpost, lnprior, lnlike;
+};
+
+// host helpers (iso_lnpost.cu)
+int iso_row_grids_fill(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, IsoRowGrids *out, size_t *smem_bytes);
+int iso_check_lnpost_handles(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, const iso_models *models);
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double iso_gauss(const IsoGaussDev &g, double model_val)
+{
+    double resid = g.val - model_val;
+    return g.c - 0.5 * resid * resid * g.h;
+}
+
+__device__ __forceinline__ double iso_sel5(const double (&a)[5], int i)
+{
+    return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : i == 3 ? a[3] : a[4];
+}
+
+template <int NDIM>
+__device__ __forceinline__ bool iso_locate_smem(const IsoGridDev &g, const double2 *smem, const int (&soff)[ISO_MAX_DIM],
+                                                const double (&x)[NDIM], int (&idx)[NDIM], double (&y)[NDIM])
+{
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) ok = ok && iso_in_bounds(g.ax[d], x[d]);
+    if (!ok) return false;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) idx[d] = iso_axis_locate(g.ax[d], smem + soff[d], x[d], y[d]);
+    return true;
+}
+
+// Stage the tables of the non-closed-form axes in shared memory (loops fully unrolled: the parameter block must
+// only be indexed with compile-time constants or it is copied to local memory).  Ends with __syncthreads().
+__device__ __forceinline__ void iso_stage_axis_tables(const IsoRowGrids &G, double2 *s_nodes)
+{
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const int so = G.smem_axis_off[0][d];
+        if (so >= 0)
+            for (int t = threadIdx.x; t < G.mg.ax[d].n; t += blockDim.x) s_nodes[so + t] = G.mg.nodes[G.mg.ax[d].off + t];
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int so = G.smem_axis_off[1][d];
+        if (so >= 0)
+            for (int t = threadIdx.x; t < G.bg.ax[d].n; t += blockDim.x) s_nodes[so + t] = G.bg.nodes[G.bg.ax[d].off + t];
+    }
+    __syncthreads();
+}
+
+// One row.  want_prior / want_like: the caller asked for the separate lnprior / lnlike values (every term is then
+// evaluated, as BasicStarModel.lnprior / lnlike would); otherwise rows whose prior is already known to be
+// non-finite return lnpost = -inf early, which is exactly what StarModel.lnpost returns (starmodel.py:540-541).
+template <int NSTARS, int PROFILE, bool TRACK>
+__device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, const double2 *s_nodes, const IsoModelDev &m,
+                                                       const double (&p)[NSTARS + 4], bool want_prior, bool want_like)
+{
+    constexpr bool DEF = PROFILE == ISO_PROFILE_DEFAULT;
+    const IsoGridDev &mg = G.mg;
+    const IsoGridDev &bg = G.bg;
+    const double nan = iso_nan();
+    const double neg_inf = iso_neg_inf();
+    const bool want_parts = want_prior || want_like;
+    const int bc_chunks = bg.ncols >> 2;
+    IsoRowResult out;
+    out.lnpost = neg_inf;
+    out.lnprior = nan;
+    out.lnlike = nan;
+    {
+        const double other = p[NSTARS], feh_in = p[NSTARS + 1], dist = p[NSTARS + 2], AV = p[NSTARS + 3];
+
+        // ---- priors that need no grid access; order of the final sum follows param_names ----------------
+        bool order_bad = false;   // starmodel.py:1618-1623 (N = 3 precedence as written in the reference)
+        if (NSTARS == 2) order_bad = p[1] > p[0];
+        if (NSTARS == 3) order_bad = !(p[0] > p[1]) && (p[1] > p[2]);
+        // track grids (mass, eep, feh, ..): p[0] is the mass (prior "mass") and `other` the EEP;
+        // isochrone grids (eep_0.., age, feh, ..): p[k] are the EEPs and `other` the age (prior "age")
+        double lnp_other, lnp_feh, lnp_dist, lnp_AV, lnd = 0.0;
+        if (DEF) {
+            lnp_other = TRACK ? iso_broken2_lnpdf<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.mass, p[0])
+                              : iso_leaf_lnpdf<ISO_PRIOR_FLATLOG>(m.age.self, other);
+            lnp_feh = iso_leaf_lnpdf<ISO_PRIOR_FEH>(m.feh.self, feh_in);
+            lnd = log(dist);   // shared by the distance prior and the distance modulus
+            lnp_dist = iso_leaf_lnpdf<ISO_PRIOR_POWERLAW, true>(m.distance.self, dist, lnd);
+            lnp_AV = iso_leaf_lnpdf<ISO_PRIOR_FLAT>(m.AV.self, AV);
+        } else {
+            lnp_other = TRACK ? iso_prior_lnpdf_dyn(&m.mass, p[0]) : iso_prior_lnpdf_dyn(&m.age, other);
+            lnp_feh = iso_prior_lnpdf_dyn(&m.feh, feh_in);
+            lnp_dist = iso_prior_lnpdf_dyn(&m.distance, dist);
+            lnp_AV = iso_prior_lnpdf_dyn(&m.AV, AV);
+        }
+        const double cheap = lnp_other + lnp_feh + lnp_dist + lnp_AV;
+        if (!want_parts && (order_bad || !isfinite(cheap))) {
+            // lnprior is already known to be -inf or NaN: StarModel.lnpost returns -inf (starmodel.py:540-541)
+            return out;
+        }
+
+        // ---- model-grid gather per star --------------------------------------------------------------
+        double lnp_eep[NSTARS], Mbol[NSTARS], y4[NSTARS][4];
+        int idx4[NSTARS][4];
+        bool bc_ok[NSTARS];
+        double Teff = nan, logg = nan, feh_s = nan, nu_max = nan, delta_nu = nan;
+#pragma unroll
+        for (int k = 0; k < NSTARS; k++) {
+            // star k uses [pars[k], shared parameters...]  (likelihood.py:43-54)
+            // model-grid coordinates pars[index_order[0..2]] (models.py:669, 696): tracks (feh, mass, eep), isochrones
+            // (age, feh, eep) — fixed by the grid kind, checked on the host
+            const double x[3] = {TRACK ? feh_in : other, TRACK ? p[0] : feh_in, TRACK ? other : p[k]};
+            double y[3];
+            int idx[3];
+            double v[8] = {nan, nan, nan, nan, nan, nan, nan, nan};
+            if (iso_locate_smem<3>(mg, s_nodes, G.smem_axis_off[0], x, idx, y)) {
+                unsigned node[8];
+                double w[8];
+                iso_corners<3>(mg, idx, y, node, w);
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double *base = mg.g + (size_t)node[j] * ISO_MP_NCOLS;
+                    iso_d4 lo = iso_ldg256(base), hi = iso_ldg256(base + 4);
+                    v[0] = fma(lo.x, w[j], v[0]);
+                    v[1] = fma(lo.y, w[j], v[1]);
+                    v[2] = fma(lo.z, w[j], v[2]);
+                    v[3] = fma(lo.w, w[j], v[3]);
+                    v[4] = fma(hi.x, w[j], v[4]);
+                    v[5] = fma(hi.y, w[j], v[5]);
+                    v[6] = fma(hi.z, w[j], v[6]);
+                    v[7] = fma(hi.w, w[j], v[7]);
+                }
+            }
+            // EEP_prior.lnpdf: BoundedPrior.lnpdf :131-140 -> Prior.pdf :54-59 -> EEP_prior._pdf :423-429
+            const double eep = TRACK ? other : p[k];
+            if (m.eep_has_bounds && iso_outside(eep, m.eep_lo, m.eep_hi)) {
+                lnp_eep[k] = neg_inf;
+            } else if (DEF && TRACK) {
+                // orig_prior = FlatLogPrior on log10 age: pdf = k2 10^age inside its bounds, so
+                // log(pdf * deriv / norm) = age ln10 + log(k2 deriv / norm); 0 -> -inf, negative / NaN -> NaN as in
+                // `np.log(pdf) if pdf else -np.inf`
+                const iso_prior_leaf &op = m.eep_orig.self;
+                const double age = v[ISO_MP_ORIG];
+                if ((op.flags & ISO_PF_HAS_BOUNDS) && iso_outside(age, op.lo, op.hi))
+                    lnp_eep[k] = neg_inf;
+                else
+                    lnp_eep[k] = fma(age, op.k[0], iso_log_or_neginf(op.k[2] * v[ISO_MP_DERIV] * m.eep_inv_norm));
+            } else {
+                double pdf = DEF ? iso_broken2_call<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.eep_orig, v[ISO_MP_ORIG])
+                                 : iso_prior_call_dyn(&m.eep_orig, v[ISO_MP_ORIG]);
+                lnp_eep[k] = iso_log_or_neginf(pdf * v[ISO_MP_DERIV] * m.eep_inv_norm);
+            }
+            Mbol[k] = v[ISO_MP_MBOL];
+            if (k == 0) {   // companions' Teff / logg / feh are discarded (likelihood.py:76, 96)
+                Teff = v[ISO_MP_TEFF];
+                logg = v[ISO_MP_LOGG];
+                feh_s = v[ISO_MP_FEH];
+                nu_max = v[ISO_MP_NU_MAX];
+                delta_nu = v[ISO_MP_DELTA_NU];
+            }
+            // BC cell of this star: interp_value_4d(Teff, logg, feh, AV)  mags.py:49-50
+            const double x4[4] = {v[ISO_MP_TEFF], v[ISO_MP_LOGG], v[ISO_MP_FEH], AV};
+            bc_ok[k] = iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[k], y4[k]);
+        }
+
+        // ---- lnprior: sum in param_names order (models.py:665, 692; starmodel.py:1510-1518) ----------------
+        double lnprior;
+        if (order_bad) {
+            lnprior = neg_inf;
+        } else {
+            lnprior = 0.0;
+            if (TRACK) {   // (mass, eep, feh, distance, AV)
+                lnprior += lnp_other;
+                lnprior += lnp_eep[0];
+            } else {                    // (eep_0 .. eep_{N-1}, age, feh, distance, AV)
+#pragma unroll
+                for (int k = 0; k < NSTARS; k++) lnprior += lnp_eep[k];
+                lnprior += lnp_other;
+            }
+            lnprior += lnp_feh;
+            lnprior += lnp_dist;
+            lnprior += lnp_AV;
+        }
+        out.lnprior = lnprior;
+        const bool prior_ok = isfinite(lnprior);
+        if (!prior_ok && !want_like) {
+            return out;
+        }
+
+        // ---- lnlike -----------------------------------------------------------------------------------
+        double ll = 0.0;
+        if (m.spec_mask & 1) ll += iso_gauss(m.spec[0], Teff);
+        if (m.spec_mask & 2) ll += iso_gauss(m.spec[1], logg);
+        if (m.spec_mask & 4) ll += iso_gauss(m.spec[2], feh_s);
+        if (m.obs_mask) {
+            // mags.py:52: 5 log10(d / 10); the default profile already holds log(d)
+            const double dist_mod = DEF ? 5.0 * fma(lnd, 0.43429448190325182765, -1.0) : 5.0 * log10(dist / 10.0);
+            for (int ch = 0; ch < bc_chunks; ch++) {
+                const int cm = (m.obs_mask >> (4 * ch)) & 0xF;
+                if (!cm) continue;
+                double tot[4];
+                double flux[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < NSTARS; k++) {
+                    double mg4[4] = {nan, nan, nan, nan};
+                    if (bc_ok[k]) {
+                        unsigned node[16];
+                        double w[16];
+                        iso_corners<4>(bg, idx4[k], y4[k], node, w);
+                        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            iso_d4 q = iso_ldg256(bg.g + (size_t)node[j] * bg.ncols + 4 * ch);
+                            b0 = fma(q.x, w[j], b0);
+                            b1 = fma(q.y, w[j], b1);
+                            b2 = fma(q.z, w[j], b2);
+                            b3 = fma(q.w, w[j], b3);
+                        }
+                        const double mb = Mbol[k] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
+                        mg4[0] = mb - b0;
+                        mg4[1] = mb - b1;
+                        mg4[2] = mb - b2;
+                        mg4[3] = mb - b3;
+                    }
+                    if (NSTARS == 1) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) tot[b] = mg4[b];
+                    } else {   // fast_addmags utils.py:67-75 — only evaluated for observed columns
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (!(cm & (1 << b))) continue;
+                    if (NSTARS > 1) tot[b] = -2.5 * log10(flux[b]);
+                    ll += iso_gauss(m.mag[4 * ch + b], tot[b]);
+                }
+            }
+        }
+        if (m.has_plax) ll += iso_gauss(m.plax, 1000.0 / dist);   // starmodel.py:1599-1601
+        if (m.has_nu_max) {                                        // starmodel.py:1604-1612
+            ll += iso_gauss(m.nu_max, nu_max);
+            if (m.has_delta_nu) ll += iso_gauss(m.delta_nu, delta_nu);
+        }
+        out.lnlike = ll;
+        out.lnpost = prior_ok ? lnprior + ll : neg_inf;   // starmodel.py:538-542
+    }
+    return out;
+}
+
+#endif  // __CUDACC__

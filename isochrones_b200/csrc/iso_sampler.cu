@@ -1,26 +1,321 @@
-// isochrones_b200 — on-device ensemble sampler.  Not built yet: the entry points exist so the
-// ABI is complete and fail loudly.
-#include "iso_common.cuh"
+// isochrones_b200 — on-device affine-invariant ensemble sampler (the emcee "stretch move", Goodman & Weare 2010).
+//
+// The reference drives its fits through emcee.EnsembleSampler(nwalkers, npars, mod.lnpost) (starmodel.py:966):
+// per half-step emcee proposes nwalkers/2 points and calls lnpost on each from Python.  emcee itself is third-party
+// and un-vendored (setup.py:60, unpinned); the algorithm restated here is its published stretch move:
+//     z = ((a - 1) u + 1)^2 / a,   q = c_j - z (c_j - x_k),   accept iff  ln u' < (ndim - 1) ln z + lnpost(q) - lnpost(x_k)
+// with c_j drawn uniformly from the complementary half of the ensemble, halves updated in turn.
+//
+// B200 mapping: ONE persistent CTA per chain, one thread per walker of the active half.  Walker positions and
+// log-probabilities live in shared memory for the whole run, the two half-steps are separated by __syncthreads(),
+// and lnpost is the same device function the batch kernel uses (iso_lnpost_row.cuh) — so a 256-walker x 2000-step
+// fit is one kernel launch instead of 4000 batches of 128 rows, and many chains (catalog mode: one star per chain)
+// fill the GPU.  Randomness is counter-based (Philox4x32-10 keyed by seed, counter = step / half / walker / chain),
+// so a run is reproducible and independent of scheduling; tests replay the same stream on the host.
+#include "iso_lnpost_row.cuh"
+
+struct iso_sampler {
+    const iso_grid *mp = nullptr, *bp = nullptr;
+    const iso_models *models = nullptr;
+    int device = 0;
+    int n_chains = 0, n_walkers = 0, ndim = 0;
+    uint64_t seed = 0;
+    double a = 2.0;
+    long long step = 0;             // full ensemble steps taken so far (RNG counter)
+    double *d_pos = nullptr;        // [n_chains, n_walkers, ndim]
+    double *d_lnprob = nullptr;     // [n_chains, n_walkers]
+    unsigned long long *d_acc = nullptr;   // [n_chains] accepted proposals
+};
+
+struct IsoSamplerParams {
+    IsoRowGrids G;
+    const IsoModelDev *models;
+    int n_models;
+    int n_chains, n_walkers, n_steps, thin;
+    long long step0;
+    unsigned long long seed;
+    double a;
+    double *pos, *lnprob;
+    double *chain_out, *lnprob_out;   // [n_steps / thin, n_chains, n_walkers, (ndim)] or NULL
+    unsigned long long *accepted;
+    IsoModelDev model;                // the single model (n_models == 1)
+};
+
+__device__ __forceinline__ void iso_philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                                  unsigned (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// 53-bit uniform in [0, 1) from two 32-bit words
+__device__ __forceinline__ double iso_u01(unsigned hi, unsigned lo)
+{
+    return (double)((((unsigned long long)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK>
+__global__ void __launch_bounds__(512, 1) iso_sampler_kernel(const __grid_constant__ IsoSamplerParams P)
+{
+    constexpr int NDIMP = NSTARS + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
+    double *s_pos = reinterpret_cast<double *>(smem_raw + sizeof(double2) * (P.G.smem_nodes > 0 ? P.G.smem_nodes : 1));
+    double *s_lp = s_pos + (size_t)P.n_walkers * NDIMP;
+
+    const int chain = blockIdx.x;
+    const int nhalf = P.n_walkers >> 1;
+    const int t = threadIdx.x;
+    const IsoModelDev &m = CATALOG ? P.models[chain % P.n_models] : P.model;
+    double *g_pos = P.pos + (size_t)chain * P.n_walkers * NDIMP;
+    double *g_lp = P.lnprob + (size_t)chain * P.n_walkers;
+
+    for (int i = t; i < P.n_walkers * NDIMP; i += blockDim.x) s_pos[i] = g_pos[i];
+    for (int i = t; i < P.n_walkers; i += blockDim.x) s_lp[i] = g_lp[i];
+    iso_stage_axis_tables(P.G, s_nodes);   // ends with __syncthreads()
+
+    unsigned long long n_acc = 0;
+    const unsigned k0 = (unsigned)(P.seed & 0xffffffffu), k1 = (unsigned)(P.seed >> 32);
+    for (int s = 0; s < P.n_steps; s++) {
+        const unsigned long long gstep = (unsigned long long)(P.step0 + s);
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            if (t < nhalf) {
+                const int k = half * nhalf + t;            // walker being moved
+                const int other0 = (1 - half) * nhalf;     // first walker of the complementary half
+                unsigned r[4], r2[4];
+                const unsigned ctr0 = (unsigned)(gstep * 2 + half), ctr1 = (unsigned)((gstep * 2 + half) >> 32);
+                iso_philox4x32_10(ctr0, ctr1 ^ ((unsigned)chain << 8), (unsigned)k, 0u, k0, k1, r);
+                iso_philox4x32_10(ctr0, ctr1 ^ ((unsigned)chain << 8), (unsigned)k, 1u, k0, k1, r2);
+                const double u = iso_u01(r[0], r[1]);
+                const int j = other0 + (int)(r[2] % (unsigned)nhalf);
+                const double u_acc = iso_u01(r2[0], r2[1]);
+                // z = ((a - 1) u + 1)^2 / a — unfused so that a host replay of the stream is bit-identical
+                const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+                const double z = __ddiv_rn(__dmul_rn(zr, zr), P.a);
+                double q[NDIMP];
+#pragma unroll
+                for (int d = 0; d < NDIMP; d++) {
+                    const double c = s_pos[j * NDIMP + d], x = s_pos[k * NDIMP + d];
+                    q[d] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), z));
+                }
+                const IsoRowResult res = iso_lnpost_row<NSTARS, PROFILE, TRACK>(P.G, s_nodes, m, q, false, false);
+                const double lnpdiff = (NDIMP - 1) * log(z) + res.lnpost - s_lp[k];
+                if (lnpdiff > log(u_acc)) {   // NaN compares false: a NaN lnpost (BC grid out of range) is a rejection
+#pragma unroll
+                    for (int d = 0; d < NDIMP; d++) s_pos[k * NDIMP + d] = q[d];
+                    s_lp[k] = res.lnpost;
+                    n_acc++;
+                }
+            }
+            __syncthreads();
+        }
+        if (P.thin > 0 && (s + 1) % P.thin == 0) {
+            const long long keep = (s + 1) / P.thin - 1;
+            if (P.chain_out) {
+                double *o = P.chain_out + ((size_t)keep * P.n_chains + chain) * P.n_walkers * NDIMP;
+                for (int i = t; i < P.n_walkers * NDIMP; i += blockDim.x) o[i] = s_pos[i];
+            }
+            if (P.lnprob_out) {
+                double *o = P.lnprob_out + ((size_t)keep * P.n_chains + chain) * P.n_walkers;
+                for (int i = t; i < P.n_walkers; i += blockDim.x) o[i] = s_lp[i];
+            }
+        }
+    }
+    for (int i = t; i < P.n_walkers * NDIMP; i += blockDim.x) g_pos[i] = s_pos[i];
+    for (int i = t; i < P.n_walkers; i += blockDim.x) g_lp[i] = s_lp[i];
+    if (n_acc) atomicAdd(P.accepted + chain, n_acc);
+}
+
+static void sampler_free(iso_sampler *s)
+{
+    if (!s) return;
+    if (s->d_pos) cudaFree(s->d_pos);
+    if (s->d_lnprob) cudaFree(s->d_lnprob);
+    if (s->d_acc) cudaFree(s->d_acc);
+    delete s;
+}
 
 extern "C" {
 
-int iso_sampler_create(iso_ctx *ctx, const iso_grid *, const iso_grid *, const iso_models *, int, int, const double *,
-                       uint64_t, double, iso_sampler **out)
+int iso_sampler_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                       int n_chains, int n_walkers, const double *h_p0, uint64_t seed, double stretch_a, iso_sampler **out)
 {
-    if (out) *out = nullptr;
-    return iso_set_error(ctx, ISO_E_UNSUPPORTED, "iso_sampler_create: the on-device sampler is not implemented yet");
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_sampler_create: ctx is NULL");
+    ISO_REQUIRE(ctx, out, "iso_sampler_create: out is NULL");
+    *out = nullptr;
+    int rc = iso_check_lnpost_handles(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, n_chains >= 1 && h_p0, "iso_sampler_create: bad argument");
+    ISO_REQUIRE(ctx, n_walkers >= 2 && n_walkers % 2 == 0 && n_walkers <= 1024,
+                "iso_sampler_create: n_walkers must be even and at most 1024 (one thread per walker of a half)");
+    ISO_REQUIRE(ctx, stretch_a > 1.0, "iso_sampler_create: stretch scale a must exceed 1");
+    ISO_REQUIRE(ctx, models->n_models == 1 || models->n_models == n_chains,
+                "iso_sampler_create: stage one model, or one model per chain (catalog mode)");
+    IsoDeviceGuard guard(ctx->device);
+    iso_sampler *s = new iso_sampler();
+    s->mp = model_pack;
+    s->bp = bc_pack;
+    s->models = models;
+    s->device = ctx->device;
+    s->n_chains = n_chains;
+    s->n_walkers = n_walkers;
+    s->ndim = 4 + models->n_stars;
+    s->seed = seed;
+    s->a = stretch_a;
+    const size_t n_rows = (size_t)n_chains * n_walkers;
+    cudaError_t e = cudaMalloc(&s->d_pos, n_rows * s->ndim * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_lnprob, n_rows * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_acc, n_chains * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_acc, 0, n_chains * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->d_pos, h_p0, n_rows * s->ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    int *d_mor = nullptr;
+    if (e == cudaSuccess && models->n_models > 1) {   // chain c uses model c
+        std::vector<int> mor(n_rows);
+        for (size_t i = 0; i < n_rows; i++) mor[i] = (int)(i / n_walkers);
+        e = cudaMalloc(&d_mor, n_rows * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_mor, mor.data(), n_rows * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        if (d_mor) cudaFree(d_mor);
+        sampler_free(s);
+        return iso_check_cuda(ctx, e, "iso_sampler_create");
+    }
+    // lnpost of the initial ensemble through the batch kernel
+    rc = iso_lnpost_batch_device(ctx, model_pack, bc_pack, models, d_mor, s->d_pos, (int64_t)n_rows, s->d_lnprob, nullptr, nullptr);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (d_mor) cudaFree(d_mor);
+    if (rc != ISO_OK || e != cudaSuccess) {
+        sampler_free(s);
+        return rc != ISO_OK ? rc : iso_check_cuda(ctx, e, "iso_sampler_create");
+    }
+    *out = s;
+    return ISO_OK;
 }
 
-int iso_sampler_run(iso_ctx *ctx, iso_sampler *, int, int, double *, double *)
+int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double *h_chain, double *h_lnprob)
 {
-    return iso_set_error(ctx, ISO_E_UNSUPPORTED, "iso_sampler_run: the on-device sampler is not implemented yet");
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_sampler_run: ctx is NULL");
+    ISO_REQUIRE(ctx, s && n_steps >= 0 && thin >= 1, "iso_sampler_run: bad argument");
+    ISO_REQUIRE(ctx, s->device == ctx->device, "iso_sampler_run: sampler belongs to another device");
+    if (n_steps == 0) return ISO_OK;
+    IsoDeviceGuard guard(ctx->device);
+    IsoSamplerParams P;
+    size_t smem = 0;
+    int rc = iso_row_grids_fill(ctx, s->mp, s->bp, &P.G, &smem);
+    if (rc != ISO_OK) return rc;
+    smem += (size_t)s->n_walkers * (s->ndim + 1) * sizeof(double);
+    ISO_REQUIRE(ctx, smem <= 200 * 1024, "iso_sampler_run: ensemble does not fit in shared memory");
+    const long long n_keep = n_steps / thin;
+    const size_t rows = (size_t)s->n_chains * s->n_walkers;
+    double *d_chain = nullptr, *d_lp = nullptr;
+    if (h_chain && n_keep > 0) ISO_CUDA(ctx, cudaMalloc(&d_chain, (size_t)n_keep * rows * s->ndim * sizeof(double)));
+    if (h_lnprob && n_keep > 0) {
+        cudaError_t e = cudaMalloc(&d_lp, (size_t)n_keep * rows * sizeof(double));
+        if (e != cudaSuccess) {
+            if (d_chain) cudaFree(d_chain);
+            return iso_check_cuda(ctx, e, "iso_sampler_run");
+        }
+    }
+    P.models = s->models->d_models;
+    P.n_models = s->models->n_models;
+    P.model = s->models->h_first;
+    P.n_chains = s->n_chains;
+    P.n_walkers = s->n_walkers;
+    P.n_steps = n_steps;
+    P.thin = thin;
+    P.step0 = s->step;
+    P.seed = s->seed;
+    P.a = s->a;
+    P.pos = s->d_pos;
+    P.lnprob = s->d_lnprob;
+    P.chain_out = d_chain;
+    P.lnprob_out = d_lp;
+    P.accepted = s->d_acc;
+    int threads = ((s->n_walkers / 2 + 31) / 32) * 32;
+    const bool catalog = s->models->n_models > 1;
+    const bool def = s->models->profile_default, track = s->models->track;
+    cudaError_t e = cudaSuccess;
+#define ISO_SLAUNCH4(NS, CAT, PROF, TRK)                                                                               \
+    do {                                                                                                              \
+        if (smem > 48 * 1024)                                                                                         \
+            e = cudaFuncSetAttribute(iso_sampler_kernel<NS, CAT, PROF, TRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem);                                                                      \
+        if (e == cudaSuccess) iso_sampler_kernel<NS, CAT, PROF, TRK><<<s->n_chains, threads, smem, ctx->stream>>>(P);  \
+    } while (0)
+#define ISO_SLAUNCH2(NS, TRK)                                                    \
+    do {                                                                         \
+        if (catalog) {                                                           \
+            if (def) ISO_SLAUNCH4(NS, true, ISO_PROFILE_DEFAULT, TRK);           \
+            else ISO_SLAUNCH4(NS, true, ISO_PROFILE_GENERIC, TRK);               \
+        } else {                                                                 \
+            if (def) ISO_SLAUNCH4(NS, false, ISO_PROFILE_DEFAULT, TRK);          \
+            else ISO_SLAUNCH4(NS, false, ISO_PROFILE_GENERIC, TRK);              \
+        }                                                                        \
+    } while (0)
+    switch (s->models->n_stars) {
+    case 1:
+        if (track) ISO_SLAUNCH2(1, true);
+        else ISO_SLAUNCH2(1, false);
+        break;
+    case 2: ISO_SLAUNCH2(2, false); break;
+    default: ISO_SLAUNCH2(3, false); break;
+    }
+#undef ISO_SLAUNCH2
+#undef ISO_SLAUNCH4
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && d_chain)
+        e = cudaMemcpyAsync(h_chain, d_chain, (size_t)n_keep * rows * s->ndim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && d_lp)
+        e = cudaMemcpyAsync(h_lnprob, d_lp, (size_t)n_keep * rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (d_chain) cudaFree(d_chain);
+    if (d_lp) cudaFree(d_lp);
+    if (e != cudaSuccess) return iso_check_cuda(ctx, e, "iso_sampler_run");
+    s->step += n_steps;
+    return ISO_OK;
 }
 
-int iso_sampler_state(iso_ctx *ctx, iso_sampler *, double *, double *, int64_t *, int64_t *)
+int iso_sampler_state(iso_ctx *ctx, iso_sampler *s, double *h_pos, double *h_lnprob, int64_t *n_accepted, int64_t *n_proposed)
 {
-    return iso_set_error(ctx, ISO_E_UNSUPPORTED, "iso_sampler_state: the on-device sampler is not implemented yet");
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_sampler_state: ctx is NULL");
+    ISO_REQUIRE(ctx, s, "iso_sampler_state: sampler is NULL");
+    IsoDeviceGuard guard(ctx->device);
+    const size_t rows = (size_t)s->n_chains * s->n_walkers;
+    if (h_pos) ISO_CUDA(ctx, cudaMemcpyAsync(h_pos, s->d_pos, rows * s->ndim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_lnprob) ISO_CUDA(ctx, cudaMemcpyAsync(h_lnprob, s->d_lnprob, rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> acc(s->n_chains);
+    ISO_CUDA(ctx, cudaMemcpyAsync(acc.data(), s->d_acc, s->n_chains * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    ISO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_accepted)   // [n_chains]
+        for (int c = 0; c < s->n_chains; c++) n_accepted[c] = (int64_t)acc[c];
+    if (n_proposed) *n_proposed = (int64_t)s->step * s->n_walkers;   // per chain
+    return ISO_OK;
 }
 
-int iso_sampler_destroy(iso_ctx *, iso_sampler *) { return ISO_OK; }
+int iso_sampler_destroy(iso_ctx *ctx, iso_sampler *s)
+{
+    if (!s) return ISO_OK;
+    IsoDeviceGuard guard(s->device);
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    sampler_free(s);
+    return ISO_OK;
+}
 
 }  // extern "C"

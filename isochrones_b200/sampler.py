@@ -1,0 +1,112 @@
+"""On-device ensemble sampler — the GPU-side replacement for the reference's emcee driver loop
+(``starmodel.py:889-972`` ``fit_mcmc_old``: ``emcee.EnsembleSampler(nwalkers, npars, self.lnpost)``, ``run_mcmc``).
+
+``DeviceEnsembleSampler`` runs emcee's stretch move (a = 2 by default) with one persistent CTA per chain
+(``iso_sampler_*`` in the C ABI): all ``n_steps`` of a run are ONE kernel launch, walkers stay in shared memory, and
+``lnpost`` is the same device code the batch path uses.  ``n_chains`` independent ensembles run concurrently — with a
+catalog-compiled model (one star model per chain) this is the "10k stars" mode.
+
+Attribute names follow emcee 2.x as the reference uses them (``chain`` [walkers, steps, ndim], ``lnprobability``,
+``acceptance_fraction``) for the single-chain case.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceEnsembleSampler(object):
+    def __init__(self, compiled, n_walkers, p0, seed=0, a=2.0, n_chains=1):
+        """``compiled``: ``CompiledModel`` (``BasicStarModel.compiled`` or ``compile_catalog(...)[0]``);
+        ``p0``: initial walkers ``[n_walkers, ndim]`` or ``[n_chains, n_walkers, ndim]``."""
+        self.compiled = compiled
+        self.ctx = compiled.ctx
+        self.ndim = compiled.ndim
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        if p0.ndim == 2:
+            p0 = p0[None]
+        if p0.shape != (n_chains, n_walkers, self.ndim):
+            raise ValueError("p0 must be [n_chains=%d, n_walkers=%d, ndim=%d], got %r"
+                             % (n_chains, n_walkers, self.ndim, p0.shape))
+        if compiled.n_models not in (1, n_chains):
+            raise ValueError("compile one model, or one model per chain")
+        self.n_chains, self.n_walkers = int(n_chains), int(n_walkers)
+        self.handle = C.c_void_p()
+        self.ctx.check(_lib.lib().iso_sampler_create(
+            self.ctx.handle, compiled.model_pack.handle, compiled.bc_pack.handle, compiled.handle, self.n_chains,
+            self.n_walkers, _lib.dp(p0), C.c_uint64(int(seed)), float(a), C.byref(self.handle)))
+        self._chains = []
+        self._lnprobs = []
+        self.n_steps = 0
+
+    def run_mcmc(self, n_steps, thin=1, store=True):
+        """Advance every chain by ``n_steps`` ensemble steps (one launch).  Returns ``(pos, lnprob)`` like emcee."""
+        n_keep = n_steps // thin
+        chain = np.empty((n_keep, self.n_chains, self.n_walkers, self.ndim)) if store else None
+        lnp = np.empty((n_keep, self.n_chains, self.n_walkers)) if store else None
+        self.ctx.check(_lib.lib().iso_sampler_run(
+            self.ctx.handle, self.handle, int(n_steps), int(thin), _lib.dp(chain) if store else None,
+            _lib.dp(lnp) if store else None))
+        if store:
+            self._chains.append(chain)
+            self._lnprobs.append(lnp)
+        self.n_steps += n_steps
+        return self.state()[:2]
+
+    def reset(self):
+        """Forget the stored samples (walker positions are kept), as ``emcee.EnsembleSampler.reset``."""
+        self._chains, self._lnprobs = [], []
+
+    def state(self):
+        pos = np.empty((self.n_chains, self.n_walkers, self.ndim))
+        lnp = np.empty((self.n_chains, self.n_walkers))
+        acc = np.zeros(self.n_chains, dtype=np.int64)
+        prop = C.c_int64()
+        self.ctx.check(_lib.lib().iso_sampler_state(self.ctx.handle, self.handle, _lib.dp(pos), _lib.dp(lnp),
+                                                    acc.ctypes.data_as(_lib.c_int64_p), C.byref(prop)))
+        return pos, lnp, acc, prop.value
+
+    # ---- stored samples ------------------------------------------------------------------------------------------
+    @property
+    def chains(self):
+        """``[n_kept, n_chains, n_walkers, ndim]``"""
+        if not self._chains:
+            return np.empty((0, self.n_chains, self.n_walkers, self.ndim))
+        return np.concatenate(self._chains, axis=0)
+
+    @property
+    def lnprobs(self):
+        if not self._lnprobs:
+            return np.empty((0, self.n_chains, self.n_walkers))
+        return np.concatenate(self._lnprobs, axis=0)
+
+    @property
+    def chain(self):
+        """emcee 2.x layout ``[n_walkers, n_kept, ndim]`` of chain 0 (``sampler.chain``, starmodel.py:952-969)."""
+        return np.transpose(self.chains[:, 0], (1, 0, 2))
+
+    @property
+    def lnprobability(self):
+        return np.transpose(self.lnprobs[:, 0], (1, 0))
+
+    @property
+    def flatchain(self):
+        return self.chain.reshape(-1, self.ndim)
+
+    @property
+    def acceptance_fraction(self):
+        """Per chain: accepted / proposed."""
+        _, _, acc, prop = self.state()
+        return acc / max(prop, 1)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().iso_sampler_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -316,6 +316,23 @@ class BasicStarModel(object):
         n = self.n_params
         return self.lnpost([cube[i] for i in range(n)])
 
+    def fit_mcmc(self, nwalkers=200, nburn=100, niter=200, p0=None, seed=0, thin=1, a=2.0):
+        """emcee-style fit on the device (the reference's ``fit_mcmc_old``, starmodel.py:889-972: burn-in, reset,
+        production run) — two kernel launches in total.  Initial walkers come from ``sample_from_prior`` as the
+        reference's emcee3 driver does (``fit.py:86``).  Returns the ``DeviceEnsembleSampler`` (``.chain``,
+        ``.lnprobability``, ``.acceptance_fraction`` as in emcee 2.x)."""
+        from .sampler import DeviceEnsembleSampler
+
+        if p0 is None:
+            p0 = self.sample_from_prior(nwalkers, values=True, require_valid=True)
+        sampler = DeviceEnsembleSampler(self.compiled, nwalkers, p0, seed=seed, a=a)
+        if nburn > 0:
+            sampler.run_mcmc(nburn, store=False)
+            sampler.reset()
+        sampler.run_mcmc(niter, thin=thin)
+        self._sampler = sampler
+        return sampler
+
     def sample_from_prior(self, n, values=False, require_valid=True):
         """Prior draws, re-drawn until ``lnpost`` is finite (starmodel.py:1716-1748); host RNG, batched validity check."""
         import pandas as pd

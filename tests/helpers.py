@@ -161,3 +161,72 @@ def product_prior_cases():
     ab.bounds = (5, 10.13)
     cases["age_bounded"] = ab
     return cases
+
+
+# ---------------------------------------------------------------------------
+# host replay of the on-device sampler's random stream (isochrones_b200/csrc/iso_sampler.cu): the same
+# Philox4x32-10 counters, so a test can re-run the stretch move on the CPU with the oracle's lnpost
+# ---------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (Salmon et al. 2011); all arguments are uint32 arrays / scalars."""
+    c = [np.asarray(x, dtype=np.uint64) for x in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def u01(hi, lo):
+    return (((hi << np.uint64(32)) | lo) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def stream(seed, gstep, half, walkers, chain):
+    """``(u_z, j_offset_raw, u_accept)`` for the given walkers of one half-step — the device kernel's draws."""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    ctr = gstep * 2 + half
+    c0 = np.uint32(ctr & 0xFFFFFFFF)
+    c1 = np.uint32(((ctr >> 32) & 0xFFFFFFFF) ^ ((chain << 8) & 0xFFFFFFFF))
+    w = np.asarray(walkers, dtype=np.uint32)
+    r = philox4x32_10(c0, c1, w, np.uint32(0), k0, k1)
+    r2 = philox4x32_10(c0, c1, w, np.uint32(1), k0, k1)
+    return u01(r[0], r[1]), r[2], u01(r2[0], r2[1])
+
+
+def replay_stretch_move(lnpost_fn, p0, n_steps, seed, a=2.0, chain=0):
+    """emcee stretch move driven by the kernel's random stream; ``lnpost_fn(rows[n, ndim]) -> [n]``.
+    Returns (chain[n_steps, n_walkers, ndim], lnprob[n_steps, n_walkers], n_accepted)."""
+    pos = np.array(p0, dtype=np.float64)
+    n_walkers, ndim = pos.shape
+    nhalf = n_walkers // 2
+    lp = lnpost_fn(pos)
+    out = np.empty((n_steps, n_walkers, ndim))
+    out_lp = np.empty((n_steps, n_walkers))
+    n_acc = 0
+    for s in range(n_steps):
+        for half in range(2):
+            ks = np.arange(half * nhalf, (half + 1) * nhalf)
+            other0 = (1 - half) * nhalf
+            u, jraw, uacc = stream(seed, s, half, ks, chain)
+            js = other0 + (jraw % np.uint64(nhalf)).astype(int)
+            zr = (a - 1.0) * u + 1.0
+            z = zr * zr / a
+            c = pos[js]
+            q = c - (c - pos[ks]) * z[:, None]
+            lq = lnpost_fn(q)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lnpdiff = (ndim - 1) * np.log(z) + lq - lp[ks]
+                acc = lnpdiff > np.log(uacc)
+            pos[ks[acc]] = q[acc]
+            lp[ks[acc]] = lq[acc]
+            n_acc += int(acc.sum())
+        out[s] = pos
+        out_lp[s] = lp
+    return out, out_lp, n_acc
