@@ -19,7 +19,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -86,84 +85,97 @@ def scattered_batch(n, seed):
     return p
 
 
-class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons sampled DURING the timed regions (NVML polled every ~2 ms; nvidia-smi fallback)."""
+_POLLER = r"""
+import sys, time
+idx = int(sys.argv[1])
+names = []
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    bits = [(nv.nvmlClocksEventReasonHwSlowdown, 'hw_slowdown'), (nv.nvmlClocksEventReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+            (nv.nvmlClocksEventReasonSwThermalSlowdown, 'sw_thermal_slowdown'), (nv.nvmlClocksEventReasonSwPowerCap, 'sw_power_cap'),
+            (nv.nvmlClocksEventReasonHwPowerBrakeSlowdown, 'hw_power_brake_slowdown')]
+    print('ready', smax, flush=True)
+    while True:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            pw, mask = -1.0, 0
+        r = '|'.join(n for b, n in bits if mask & b)
+        print('%.6f,%d,%.1f,%s' % (time.time(), sm, pw, r), flush=True)
+        time.sleep(0.001)
+except Exception as e:
+    print('error', repr(e), flush=True)
+"""
+
+
+class ClockSampler(object):
+    """SM clock / throttle reasons sampled DURING the timed regions by a separate NVML polling process (~1 kHz), so
+    that the sampling neither holds this process's GIL nor delays its kernel launches.  `mark()` brackets the timed
+    regions; only samples inside a bracket are summarised."""
 
     def __init__(self, device):
-        super().__init__(daemon=True)
-        self.device = device
-        self.sm, self.power, self.reasons = [], [], set()
-        self.sm_max = None
-        self.stop_flag = threading.Event()
-        self.source = "nvml"
-
-    def _run_nvml(self):
-        import pynvml as nv
-
-        nv.nvmlInit()
-        # LOCAL_RANK indexes the visible devices; map through CUDA_VISIBLE_DEVICES when it is a plain index list
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = self.device
+        idx = device
         if vis:
             try:
-                idx = int(vis.split(",")[self.device])
+                idx = int(vis.split(",")[device])
             except (ValueError, IndexError):
-                idx = self.device
-        h = nv.nvmlDeviceGetHandleByIndex(idx)
-        self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
-                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
-                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
-        while not self.stop_flag.is_set():
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-            try:
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.002)
-
-    def _run_smi(self):
-        self.source = "nvidia-smi"
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.sm.append(float(parts[0]))
-                    self.sm_max = float(parts[1])
-                    self.power.append(float(parts[2]))
-                    for i, n in enumerate(names):
-                        if parts[3 + i].lower().startswith("active"):
-                            self.reasons.add(n)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.05)
-
-    def run(self):
+                idx = device
+        self.windows = []
+        self.sm_max = None
+        self.proc = None
         try:
-            self._run_nvml()
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLLER, str(idx)], stdout=subprocess.PIPE, text=True)
+            first = self.proc.stdout.readline().split()
+            if first and first[0] == "ready":
+                self.sm_max = float(first[1])
+            else:
+                self.proc.kill()
+                self.proc = None
         except Exception:
-            self._run_smi()
+            self.proc = None
+
+    def start(self):
+        pass
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "source": self.source}
-        sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-                "samples": len(sm), "power_w_max": max(self.power) if self.power else None, "source": self.source,
-                "window": "device-timed loop + end-to-end loop"}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        time.sleep(0.005)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, power, reasons = [], [], set()
+        for ln in out.splitlines():
+            parts = ln.split(",")
+            if len(parts) != 4:
+                continue
+            try:
+                t = float(parts[0])
+            except ValueError:
+                continue
+            if not any(a <= t <= b for a, b in self.windows):
+                continue
+            sm.append(float(parts[1]))
+            power.append(float(parts[2]))
+            reasons.update(x for x in parts[3].split("|") if x)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "source": "nvml"}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power), "source": "nvml polled at ~1 kHz by a side process",
+                "window": "samples inside the device-timed loop and the end-to-end loop only"}
 
 
 def cpu_baseline(trk, bc, ic_host_model, mg, bg, seed, budget_s=12.0):
@@ -231,6 +243,76 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def extra_workloads(ctx, bc, args, peak):
+    """BASELINE.json configs 3 and 5 on one GPU (informational "alt" entries; parity for them lives in tests/):
+    binary-star lnpost batch on the isochrone grid, and the on-device ensemble sampler (256 walkers x 2000 steps as
+    one chain, and 1184 such chains x 100 steps filling the GPU)."""
+    import isochrones_b200 as ib
+    from isochrones_b200 import synthetic as syn
+    from isochrones_b200.sampler import DeviceEnsembleSampler
+
+    out = {}
+    iso = syn.make_iso_grid(columns=("Teff", "logg", "feh", "Mbol", "mass", "dm_deep", "nu_max", "delta_nu"))
+    ic = ib.ichrone_from_arrays("iso", iso, bc, ctx=ctx)
+    truth = syn.default_truth("iso", n_stars=2)
+    _, _, _, mags = ic.interp_mag([truth[0]] + list(truth[2:]), list(BANDS))
+    obs = {b: (float(np.round(m, 3)) - 0.35, 0.02) for b, m in zip(BANDS, mags)}
+    binary = ib.BinaryStarModel(ic, Teff=(5772.0, 80.0), logg=(4.44, 0.1), feh=(0.0, 0.1), parallax=(10.0, 0.1), **obs)
+    batches = []
+    for s in range(4):
+        p = syn.posterior_like_batch("iso", BATCH, truth, seed=70 + s)
+        p[:, :2] = -np.sort(-p[:, :2], axis=1)
+        batches.append(p)
+    d_b = []
+    for b in batches:
+        d = ctx.dev_alloc(b.nbytes)
+        ctx.h2d(d, b)
+        d_b.append(d)
+    d_out = ctx.dev_alloc(BATCH * 8)
+    ms, _ = timed_device_loop(ctx, binary.compiled, d_b, d_out, args.steps, args.warmup)
+    res = np.empty(BATCH)
+    ctx.d2h(res, d_out)
+    k_ms = ms / args.steps
+    out["binary_iso_posterior_like"] = {
+        "value": BATCH / (k_ms * 1e-3), "unit": UNIT, "ms_per_step": k_ms, "finite_frac": float(np.isfinite(res).mean()),
+        "algorithmic_bytes_per_eval": 1848.0, "roofline_frac": 1848.0 * BATCH / (k_ms * 1e-3) / 1e9 / peak,
+        "config": "configs[4] on one GPU: BinaryStarModel, iso grid 107x15x1710, 4 bands + parallax, 1e6 rows"}
+    for d in d_b:
+        ctx.dev_free(d)
+
+    # single-star model on the iso grid drives the sampler runs (starfit's default grid)
+    truth1 = syn.default_truth("iso", n_stars=1)
+    _, _, _, mags1 = ic.interp_mag(list(truth1), list(BANDS))
+    single = ib.SingleStarModel(ic, Teff=(5772.0, 80.0), logg=(4.44, 0.1), feh=(0.0, 0.1), parallax=(10.0, 0.1),
+                                **{b: (float(np.round(m, 3)), 0.02) for b, m in zip(BANDS, mags1)})
+    nw, nsteps = 256, 2000
+    p0 = syn.posterior_like_batch("iso", nw, truth1, seed=4)
+    smp = DeviceEnsembleSampler(single.compiled, nw, p0, seed=4)
+    smp.run_mcmc(50, store=False)
+    t0 = time.perf_counter()
+    smp.run_mcmc(nsteps, thin=10)
+    dt = time.perf_counter() - t0
+    out["emcee_256x2000_one_chain"] = {
+        "value": nw * nsteps / dt, "unit": UNIT, "seconds": dt, "acceptance_fraction": float(smp.acceptance_fraction[0]),
+        "config": "configs[2]: stretch move a=2, 256 walkers x 2000 steps, one persistent CTA, one launch "
+                  "(latency-bound: 4000 dependent half-steps)"}
+    smp.close()
+    n_chains, steps_c = 1184, 100
+    p0c = np.stack([syn.posterior_like_batch("iso", nw, truth1, seed=1000 + c) for c in range(8)])
+    p0c = np.ascontiguousarray(np.tile(p0c, (n_chains // 8, 1, 1)))
+    smc = DeviceEnsembleSampler(single.compiled, nw, p0c, seed=5, n_chains=n_chains)
+    smc.run_mcmc(10, store=False)
+    t0 = time.perf_counter()
+    smc.run_mcmc(steps_c, store=False)
+    dt = time.perf_counter() - t0
+    out["emcee_256_walkers_x_1184_chains"] = {
+        "value": n_chains * nw * steps_c / dt, "unit": UNIT, "seconds": dt,
+        "acceptance_fraction": float(np.mean(smc.acceptance_fraction)),
+        "config": "1184 independent 256-walker ensembles x 100 steps in one launch (8 CTAs per SM)"}
+    smc.close()
+    return out
+
+
 def timed_device_loop(ctx, compiled, d_batches, d_out, steps, warmup, barrier=None):
     for s in range(warmup):
         compiled.lnpost_device(d_batches[s % len(d_batches)], BATCH, d_out)
@@ -255,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the binary-star / sampler 'alt' workloads")
     ap.add_argument("--small", action="store_true", help="small grids (debugging only; not a valid bench)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -316,7 +399,9 @@ def main():
 
     clocks = ClockSampler(local_rank)
     clocks.start()
+    tw0 = time.time()
     ms, launches = timed_device_loop(ctx, compiled, d_post, d_out, args.steps, args.warmup, barrier)
+    clocks.mark(tw0, time.time())
     ms = max_over_ranks(ms)
     value = world * BATCH * args.steps / (ms * 1e-3)
     kernel_ms = ms / args.steps
@@ -329,10 +414,12 @@ def main():
     for s in range(max(args.warmup, 3)):
         mod.lnpost_batch(h_in[s % 2], out=h_out)
     barrier()
+    tw0 = time.time()
     t0 = time.perf_counter()
     for s in range(args.steps):
         mod.lnpost_batch(h_in[s % 2], out=h_out)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks.mark(tw0, time.time())
     barrier()
     e2e_value = world * BATCH * args.steps / e2e_s
     clock_summary = clocks.summary()
@@ -386,6 +473,9 @@ def main():
                      "roofline_frac": B_ALG * BATCH / (k_ms * 1e-3) / 1e9 / peak}
         for d in d_b:
             ctx.dev_free(d)
+
+    if world == 1 and not args.no_extras:
+        alt.update(extra_workloads(ctx, bc, args, peak))
 
     achieved = B_ALG * BATCH / (kernel_ms * 1e-3) / 1e9
     traffic = None
