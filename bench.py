@@ -36,6 +36,14 @@ METRIC = "lnpost evals/sec (batched walkers)"
 UNIT = "evals/s"
 
 
+def host_threads():
+    """Host cores this process may use (the CPU arm uses all of them through OpenMP's num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_workload(ctx=None, small=False):
     """Grids, interpolator, star model and the truth point.  Needs the GPU only through ``ctx`` (None: host objects)."""
     import isochrones_b200 as ib
@@ -184,7 +192,7 @@ def cpu_baseline(trk, bc, ic_host_model, mg, bg, seed, budget_s=12.0):
     from oracle import oracle
 
     om = oracle.StarModel(ic_host_model, model_grid=mg, bc_grid=bg)
-    threads = oracle.max_threads()
+    threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     truth = syn.default_truth("track", n_eep=len(trk["axes"][2]))
     probe = syn.posterior_like_batch("track", 200_000, truth, seed=seed)
     t0 = time.perf_counter()
@@ -212,7 +220,7 @@ def run_reference(args, rank, world):
     mags, mg, bg = truth_mags(trk, bc, truth)
     mod = make_model(ic, mags)
     om = oracle.StarModel(mod, model_grid=mg, bc_grid=bg)
-    threads = oracle.max_threads()
+    threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     probe = syn.posterior_like_batch("track", 200_000, truth, seed=100)
     t0 = time.perf_counter()
     om.lnpost_batch(probe, n_threads=threads)
@@ -310,6 +318,50 @@ def extra_workloads(ctx, bc, args, peak):
         "acceptance_fraction": float(np.mean(smc.acceptance_fraction)),
         "config": "1184 independent 256-walker ensembles x 100 steps in one launch (8 CTAs per SM)"}
     smc.close()
+
+    # configs[3] in miniature on one GPU: a catalog of 10k independent star models, rows of many stars in one launch
+    import pandas as pd
+
+    from isochrones_b200.catalog import StarCatalog
+
+    n_stars, rows_per_star = 10_000, 100
+    rng = np.random.RandomState(8)
+    t = np.tile(truth1, (n_stars, 1))
+    t[:, 0] = rng.uniform(300.0, 900.0, n_stars)
+    t[:, 1] = rng.uniform(9.0, 9.9, n_stars)
+    t[:, 2] = rng.uniform(-0.5, 0.3, n_stars)
+    t[:, 3] = rng.uniform(50.0, 400.0, n_stars)
+    t[:, 4] = rng.uniform(0.0, 0.5, n_stars)
+    _, _, _, mg = ic.interp_mag([t[:, j] for j in range(5)], list(BANDS))
+    table = {"parallax": 1000.0 / t[:, 3], "parallax_unc": np.full(n_stars, 0.1)}
+    for j, b in enumerate(BANDS):
+        table[b + "_mag"] = mg[:, j]
+        table[b + "_mag_unc"] = np.full(n_stars, 0.02)
+    t0 = time.perf_counter()
+    cat = StarCatalog(pd.DataFrame(table), props=["parallax"])
+    compiled = cat.compile(ic)
+    t_compile = time.perf_counter() - t0
+    mor = np.repeat(np.arange(n_stars, dtype=np.int32), rows_per_star)
+    pars = np.repeat(t, rows_per_star, axis=0)
+    pars *= 1 + 0.002 * rng.standard_normal(pars.shape)
+    n_rows = len(pars)
+    d_p, d_m, d_o = ctx.dev_alloc(pars.nbytes), ctx.dev_alloc(mor.nbytes), ctx.dev_alloc(n_rows * 8)
+    ctx.h2d(d_p, pars)
+    ctx.h2d(d_m, mor)
+    for _ in range(3):
+        compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m)
+    k_ms = ctx.timer_stop() / args.steps
+    res = np.empty(n_rows)
+    ctx.d2h(res, d_o)
+    out["catalog_10k_stars"] = {
+        "value": n_rows / (k_ms * 1e-3), "unit": UNIT, "ms_per_step": k_ms, "finite_frac": float(np.isfinite(res).mean()),
+        "compile_seconds": t_compile,
+        "config": "configs[3] shape on one GPU: 10 000 star models (iso grid, 4 bands + parallax) in HBM, 1e6 rows "
+                  "(100 per star) in one launch through model_of_row"}
     return out
 
 

@@ -250,3 +250,36 @@ def test_custom_priors_generic_profile(world, kind, N):
     _compare(got[2], want[2], ATOL_LNPOST)
     _compare(got[0], want[0], ATOL_LNPOST)
     assert np.isfinite(want[0]).sum() > 10_000
+
+
+def test_star_catalog_compile(world):
+    """StarCatalog (table of stars) -> one device model per row; checked against per-row host models + the oracle."""
+    import pandas as pd
+
+    from isochrones_b200 import synthetic as syn
+    from isochrones_b200.catalog import StarCatalog
+    from oracle import oracle
+
+    ic = world["ic_track"]
+    rng = np.random.RandomState(3)
+    n = 300
+    truth = syn.default_truth("track")
+    t = np.tile(truth, (n, 1)) * (1 + 0.05 * rng.standard_normal((n, 5)))
+    t[:, 4] = np.abs(t[:, 4])
+    _, _, _, mags = ic.interp_mag([t[:, j] for j in range(5)], ["V", "J", "K"])
+    df = pd.DataFrame({"V_mag": mags[:, 0], "V_mag_unc": 0.02, "J_mag": mags[:, 1], "J_mag_unc": 0.03,
+                       "K_mag": mags[:, 2], "K_mag_unc": 0.03, "Teff": 5800.0 + 50 * rng.standard_normal(n), "Teff_unc": 80.0,
+                       "parallax": 1000.0 / t[:, 3], "parallax_unc": 0.1})
+    df.loc[5, "J_mag"] = np.nan
+    df.loc[9, "parallax"] = np.nan
+    cat = StarCatalog(df, props=["Teff", "parallax"])
+    compiled = cat.compile(ic)
+    assert compiled.n_models == n
+    rows_per_star = 40
+    mor = np.repeat(np.arange(n, dtype=np.int32), rows_per_star)
+    pars = np.repeat(t, rows_per_star, axis=0) * (1 + 0.01 * rng.standard_normal((n * rows_per_star, 5)))
+    got = compiled.lnpost(pars, model_of_row=mor)
+    oms = [oracle.StarModel(m, model_grid=world["og_track"], bc_grid=world["og_bc"]) for m in cat.iter_models(ic)]
+    want = oracle.lnpost_catalog(oms, mor, pars, n_threads=8)
+    _compare(got, want, ATOL_LNPOST)
+    assert np.isfinite(want).mean() > 0.9

@@ -135,3 +135,53 @@ def test_row_sharder():
         assert np.array_equal(shards[0].assemble(gathered), rows * 2.0)
     with pytest.raises(ValueError):
         RowSharder(4, 2, 2)
+
+
+def test_catalog_structs_match_per_model_structs():
+    """StarCatalog.build_structs (vectorised) == one BasicStarModel.to_struct per row (the reference's iter_models)."""
+    import pandas as pd
+
+    import isochrones_b200 as ib
+    from isochrones_b200 import synthetic as syn
+    from isochrones_b200.catalog import StarCatalog
+
+    trk = syn.make_track_grid(n_feh=3, n_mass=6, n_eep=20)
+    bc = syn.make_bc_grid(bands=("V", "J", "K"), n_teff=6, n_logg=4, n_feh=3, n_av=3)
+    ic = ib.ichrone_from_arrays("track", trk, bc)
+    rng = np.random.RandomState(0)
+    n = 12
+    df = pd.DataFrame({
+        "V_mag": 10 + rng.rand(n), "V_mag_unc": 0.02 + 0 * rng.rand(n),
+        "J_mag": 9 + rng.rand(n), "J_mag_unc": 0.03 + 0 * rng.rand(n),
+        "K_mag": 8 + rng.rand(n), "K_mag_unc": 0.03 + 0 * rng.rand(n),
+        "Teff": 5000 + 1000 * rng.rand(n), "Teff_unc": 80.0 + 0 * rng.rand(n),
+        "parallax": 5 + 5 * rng.rand(n), "parallax_unc": 0.1 + 0 * rng.rand(n),
+    })
+    df.loc[3, "J_mag"] = np.nan            # band missing for one star
+    df.loc[5, "Teff"] = np.nan             # spectroscopy missing
+    df.loc[7, "parallax"] = -0.4           # negative parallax -> bound from the uncertainty
+    df.loc[9, "parallax"] = np.nan         # no parallax -> default distance bounds
+    cat = StarCatalog(df, props=["Teff", "parallax"])
+    assert cat.bands == ("V", "J", "K")
+    arr, bands = cat.build_structs(ic, maxAV=0.7)
+    assert bands == ["V", "J", "K"] and len(arr) == n
+    col = {b: i for i, b in enumerate(bands)}
+    import ctypes as C
+
+    for i, mod in enumerate(cat.iter_models(ic)):
+        mod.set_bounds(AV=(0, 0.7))
+        want = mod.to_struct(band_columns=col)
+        got = arr[i]
+        assert got.n_bands == want.n_bands == len(mod.bands)
+        assert list(got.band_col)[:got.n_bands] == list(want.band_col)[:want.n_bands]
+        for f in ("mag_val", "mag_unc"):
+            assert list(getattr(got, f))[:got.n_bands] == list(getattr(want, f))[:want.n_bands]
+        for f in ("spec_val", "spec_unc"):
+            assert np.array_equal(np.array(getattr(got, f)), np.array(getattr(want, f)), equal_nan=True)
+        assert (got.has_plax, got.has_nu_max) == (want.has_plax, want.has_nu_max)
+        if want.has_plax:
+            assert (got.plax, got.plax_unc) == (want.plax, want.plax_unc)
+        assert (got.distance.self.lo, got.distance.self.hi) == (want.distance.self.lo, want.distance.self.hi), i
+        assert (got.AV.self.lo, got.AV.self.hi) == (0.0, 0.7)
+        assert bytes(got.mass) == bytes(want.mass) and bytes(got.feh) == bytes(want.feh)
+        assert bytes(got.eep_orig) == bytes(want.eep_orig)
