@@ -13,6 +13,12 @@
 #ifndef ISO_LNPOST_MIN_BLOCKS
 #define ISO_LNPOST_MIN_BLOCKS 2
 #endif
+#ifndef ISO_LNPOST_PREFETCH
+#define ISO_LNPOST_PREFETCH 1
+#endif
+#ifndef ISO_LNPOST_BLOCKS_PER_SM
+#define ISO_LNPOST_BLOCKS_PER_SM 2   // persistent grid: exactly the CTAs that are resident (2 per SM), rows grid-strided
+#endif
 
 struct IsoLnpostArgs {
     const IsoModelDev *models;
@@ -42,11 +48,31 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
     iso_stage_axis_tables(P.G, s_nodes);
 
     const bool want_prior = a.lnprior != nullptr, want_like = a.lnlike != nullptr;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+#if ISO_LNPOST_PREFETCH
+    // software pipelining of the row stream: the next row's parameters are requested before this row is evaluated,
+    // so their HBM latency hides behind ~2000 instructions of work
+    double pn[NDIMP];
+    if (i < a.N) {
+#pragma unroll
+        for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[i * NDIMP + j];
+    }
+#endif
+    for (; i < a.N; i += stride) {
         const IsoModelDev &m = CATALOG ? a.models[a.model_of_row[i]] : P.model;
         double p[NDIMP];
+#if ISO_LNPOST_PREFETCH
+#pragma unroll
+        for (int j = 0; j < NDIMP; j++) p[j] = pn[j];
+        if (i + stride < a.N) {
+#pragma unroll
+            for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[(i + stride) * NDIMP + j];
+        }
+#else
 #pragma unroll
         for (int j = 0; j < NDIMP; j++) p[j] = a.pars[i * NDIMP + j];
+#endif
         const IsoRowResult r = iso_lnpost_row<NSTARS, PROFILE, TRACK>(P.G, s_nodes, m, p, want_prior, want_like);
         if (want_prior) a.lnprior[i] = r.lnprior;
         if (want_like) a.lnlike[i] = r.lnlike;
@@ -177,7 +203,7 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     a.N = N;
     const bool catalog = d_model_of_row != nullptr;
     int64_t want = (N + ISO_LNPOST_THREADS - 1) / ISO_LNPOST_THREADS;
-    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;
+    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * ISO_LNPOST_BLOCKS_PER_SM;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
 #define ISO_LAUNCH4(NS, CAT, PROF, TRK)                                                                                  \
