@@ -13,6 +13,9 @@
 #ifndef ISO_LNPOST_MIN_BLOCKS
 #define ISO_LNPOST_MIN_BLOCKS 2
 #endif
+#ifndef ISO_LNPOST_MIN_BLOCKS_MULTI
+#define ISO_LNPOST_MIN_BLOCKS_MULTI 2   // binary / triple models: 128 registers + a small spill beats 1 CTA/SM at 255
+#endif
 #ifndef ISO_LNPOST_PREFETCH
 #define ISO_LNPOST_PREFETCH 1
 #endif
@@ -38,7 +41,7 @@ struct IsoLnpostParams {
 };
 
 template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK>
-__global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : ISO_LNPOST_MIN_BLOCKS_MULTI)
 iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 {
     constexpr int NDIMP = NSTARS + 4;
