@@ -2,6 +2,7 @@
 //
 // A batch of N rows is cut into chunks; chunk c runs H2D -> kernel -> D2H in order on copy_stream[c & 1], so the
 // PCIe transfers of one chunk overlap the kernel (and the opposite-direction transfer) of the other.
+#include <stdlib.h>
 #include <string.h>
 
 #include "iso_common.cuh"
@@ -33,7 +34,12 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
     if (n_rows <= 0) return ISO_OK;
     IsoDeviceGuard guard(ctx->device);
 
-    int64_t chunk = n_rows < ISO_PIPE_CHUNK_ROWS ? n_rows : ISO_PIPE_CHUNK_ROWS;
+    static const int64_t chunk_rows = [] {
+        const char *e = getenv("ISO_PIPE_CHUNK_ROWS");   // tuning knob; the default is what bench.py measures
+        long long v = e ? atoll(e) : 0;
+        return (int64_t)(v >= 1024 ? v : ISO_PIPE_CHUNK_ROWS);
+    }();
+    int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
     int64_t off[ISO_PIPE_MAX_ARRAYS + 1];
     bool pinned[ISO_PIPE_MAX_ARRAYS];
     bool active[ISO_PIPE_MAX_ARRAYS];

@@ -49,6 +49,19 @@ class DFInterpolator(object):
         self._device_grid = None
         return self
 
+    @classmethod
+    def from_npz(cls, filename, index_columns, index_names=None, ctx=None):
+        """Load a dense grid the reference cached with ``np.savez(filename, grid=grid, columns=columns)``
+        (interp.py:611-612; e.g. ``full_grid*.npz`` written by ``Grid.interp``, grid.py:132-137).  The axes are not in
+        that file (the reference takes them from ``df.index.levels``), so they are passed in."""
+        d = np.load(filename, allow_pickle=False)
+        grid = d["grid"]
+        columns = [str(c) for c in d["columns"]]
+        if grid.ndim != len(index_columns) + 1 or grid.shape[-1] != len(columns):
+            raise ValueError("grid of shape %r does not match %d axes / %d columns"
+                             % (grid.shape, len(index_columns), len(columns)))
+        return cls.from_arrays(grid, index_columns, columns, index_names=index_names, ctx=ctx)
+
     def _make_grid(self, df, recalc=False):
         # host-side, one-time data preparation (interp.py:590-614): NaN-pad a non-full index to a dense array
         if self.filename is not None and os.path.exists(self.filename) and not recalc:

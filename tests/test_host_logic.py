@@ -185,3 +185,38 @@ def test_catalog_structs_match_per_model_structs():
         assert (got.AV.self.lo, got.AV.self.hi) == (0.0, 0.7)
         assert bytes(got.mass) == bytes(want.mass) and bytes(got.feh) == bytes(want.feh)
         assert bytes(got.eep_orig) == bytes(want.eep_orig)
+
+
+def test_load_reference_npz_cache(tmp_path):
+    """DFInterpolator.from_npz reads the dense-grid cache format the reference writes (interp.py:611-612)."""
+    import itertools
+
+    import pandas as pd
+
+    from isochrones_b200 import DFInterpolator
+
+    x, y, z = np.arange(3.0), np.arange(4.0) * 2, np.arange(5.0) + 1
+    index = pd.MultiIndex.from_product((x, y, z), names=["a", "b", "c"])
+    df = pd.DataFrame(index=index)
+    df["s"] = [a + b + c for a, b, c in itertools.product(x, y, z)]
+    df["p"] = [a * b * c for a, b, c in itertools.product(x, y, z)]
+    fn = str(tmp_path / "full_grid.npz")
+    from oracle import ref_shim
+
+    if ref_shim.available():       # written by the reference itself (build container only)
+        ref = ref_shim.load()
+        ref.interp.DFInterpolator(df, filename=fn, is_full=True)
+    else:                           # same format, written by hand
+        np.savez(fn, grid=np.array(df.values, dtype=float).reshape(3, 4, 5, 2), columns=list(df.columns))
+    it = DFInterpolator.from_npz(fn, (x, y, z), index_names=["a", "b", "c"])
+    mine = DFInterpolator(df, is_full=True)
+    assert it.columns == mine.columns == ["s", "p"]
+    assert np.array_equal(it.grid, mine.grid) and it.grid.shape == (3, 4, 5, 2)
+    assert all(np.array_equal(a, b) for a, b in zip(it.index_columns, mine.index_columns))
+    # the product's own cache round trip uses the same format
+    fn2 = str(tmp_path / "mine.npz")
+    DFInterpolator(df, filename=fn2, is_full=True)
+    again = DFInterpolator(df, filename=fn2, is_full=True)
+    assert np.array_equal(again.grid, mine.grid)
+    with pytest.raises(ValueError):
+        DFInterpolator.from_npz(fn, (x, y))
