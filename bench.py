@@ -121,6 +121,30 @@ except Exception as e:
 """
 
 
+def grid_wide_batch(n, trk, seed):
+    """Rows spread over the WHOLE populated track grid (every [Fe/H], masses 0.1-100, EEPs up to the end of the
+    shorter of the bracketing tracks): the gathers touch ~200 MB of model-grid nodes, more than the 126 MB L2 — the
+    HBM-bound extreme of the kernel.  Many rows fall outside the age prior (old low-mass stars) and stop after the
+    model-grid gather."""
+    from isochrones_b200 import synthetic as syn
+
+    rng = np.random.RandomState(seed)
+    fehs, masses, eeps = trk["axes"]
+    last = np.array([[syn.max_eep_table(m, f) for m in masses] for f in fehs], dtype=float)
+    last = np.minimum(last, len(eeps))
+    cell_last = np.minimum(np.minimum(last[:-1, :-1], last[1:, :-1]), np.minimum(last[:-1, 1:], last[1:, 1:]))
+    m_hi = np.searchsorted(masses, 100.0) - 1
+    a = rng.randint(0, len(fehs) - 1, n)
+    b = rng.randint(0, m_hi, n)
+    p = np.empty((n, 5))
+    p[:, 0] = masses[b] + (masses[b + 1] - masses[b]) * rng.random_sample(n)
+    p[:, 1] = 1.0 + (cell_last[a, b] - 2.0) * rng.random_sample(n)
+    p[:, 2] = fehs[a] + (fehs[a + 1] - fehs[a]) * rng.random_sample(n)
+    p[:, 3] = rng.uniform(20.0, 199.0, n)
+    p[:, 4] = rng.uniform(0.0, 0.99, n)
+    return p
+
+
 class ClockSampler(object):
     """SM clock / throttle reasons sampled DURING the timed regions by a separate NVML polling process (~1 kHz), so
     that the sampling neither holds this process's GIL nor delays its kernel launches.  `mark()` brackets the timed
@@ -513,7 +537,8 @@ def main():
 
     alt = {}
     for name, gen in (("prior_like", lambda s: syn.prior_like_batch("track", BATCH, bounds, seed=3 + s)),
-                      ("scattered_valid", lambda s: scattered_batch(BATCH, seed=50 + s))):
+                      ("scattered_valid", lambda s: scattered_batch(BATCH, seed=50 + s)),
+                      ("grid_wide", lambda s: grid_wide_batch(BATCH, trk, seed=90 + s))):
         batches = [gen(s) for s in range(N_BATCHES)]
         d_b = stage(batches)
         ms_a, _ = timed_device_loop(ctx, compiled, d_b, d_out, args.steps, args.warmup)

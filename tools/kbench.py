@@ -16,6 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--rows", type=int, default=bench.BATCH)
+    ap.add_argument("--only", default="")
     ap.add_argument("--tag", default=os.environ.get("ISO_B200_LIB", "default"))
     args = ap.parse_args()
     from isochrones_b200 import _lib, synthetic as syn
@@ -31,10 +32,13 @@ def main():
         "posterior": lambda s: syn.posterior_like_batch("track", n, truth, n_eep=n_eep, seed=2 + s),
         "prior": lambda s: syn.prior_like_batch("track", n, bounds, seed=3 + s),
         "scattered": lambda s: bench.scattered_batch(n, seed=50 + s),
+        "grid_wide": lambda s: bench.grid_wide_batch(n, trk, seed=90 + s),
     }
     d_out = ctx.dev_alloc(n * 8)
     res = {}
     for name, gen in gens.items():
+        if args.only and name not in args.only.split(","):
+            continue
         ptrs = []
         for s in range(4):
             b = gen(s)
