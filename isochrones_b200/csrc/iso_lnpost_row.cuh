@@ -97,23 +97,78 @@ __device__ __forceinline__ bool iso_locate_smem(const IsoGridDev &g, const doubl
     return true;
 }
 
-// Stage the tables of the non-closed-form axes in shared memory (loops fully unrolled: the parameter block must
-// only be indexed with compile-time constants or it is copied to local memory).  Ends with __syncthreads().
+// ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier: SASS UBLKCP / SYNCS ------------------------------------------
+__device__ __forceinline__ unsigned iso_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void iso_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(iso_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void iso_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(iso_smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy; bytes a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void iso_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     iso_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(iso_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void iso_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " ISO_WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra ISO_DONE_%=;\n"
+        " bra ISO_WAIT_%=;\n"
+        " ISO_DONE_%=:\n"
+        "}" ::"r"(iso_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Stage the tables of the non-closed-form axes in shared memory: one elected thread arms an mbarrier with the total
+// byte count and issues one TMA bulk copy per axis table (contiguous double2 runs, 16-byte aligned on both sides);
+// every thread then waits on the barrier's phase.  The loops are fully unrolled: the parameter block must only be
+// indexed with compile-time constants or it is copied to local memory.  All threads of the CTA must call this.
 __device__ __forceinline__ void iso_stage_axis_tables(const IsoRowGrids &G, double2 *s_nodes)
 {
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const int so = G.smem_axis_off[0][d];
-        if (so >= 0)
-            for (int t = threadIdx.x; t < G.mg.ax[d].n; t += blockDim.x) s_nodes[so + t] = G.mg.nodes[G.mg.ax[d].off + t];
-    }
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-        const int so = G.smem_axis_off[1][d];
-        if (so >= 0)
-            for (int t = threadIdx.x; t < G.bg.ax[d].n; t += blockDim.x) s_nodes[so + t] = G.bg.nodes[G.bg.ax[d].off + t];
-    }
+    __shared__ __align__(8) unsigned long long tables_bar;
+    if (threadIdx.x == 0) iso_mbar_init(&tables_bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned total = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            if (G.smem_axis_off[0][d] >= 0) total += (unsigned)G.mg.ax[d].n * (unsigned)sizeof(double2);
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            if (G.smem_axis_off[1][d] >= 0) total += (unsigned)G.bg.ax[d].n * (unsigned)sizeof(double2);
+        iso_mbar_expect_tx(&tables_bar, total);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int so = G.smem_axis_off[0][d];
+            if (so >= 0)
+                iso_bulk_g2s(s_nodes + so, G.mg.nodes + G.mg.ax[d].off, (unsigned)G.mg.ax[d].n * (unsigned)sizeof(double2),
+                             &tables_bar);
+        }
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int so = G.smem_axis_off[1][d];
+            if (so >= 0)
+                iso_bulk_g2s(s_nodes + so, G.bg.nodes + G.bg.ax[d].off, (unsigned)G.bg.ax[d].n * (unsigned)sizeof(double2),
+                             &tables_bar);
+        }
+    }
+    iso_mbar_wait(&tables_bar, 0);
 }
 
 // One row.  want_prior / want_like: the caller asked for the separate lnprior / lnlike values (every term is then
