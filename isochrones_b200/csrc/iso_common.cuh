@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,7 @@ struct iso_ctx {
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaDeviceProp prop;
     std::string last_error;
+    std::recursive_mutex mu;                // entry points that touch the staging buffers / streams hold it
     int64_t launches = 0;
     // staging buffers for the host-pointer entry points (grown on demand)
     void *d_stage[2] = {nullptr, nullptr};

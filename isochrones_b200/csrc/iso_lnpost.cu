@@ -363,6 +363,7 @@ int iso_lnpost_batch_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_
     if (N == 0) return ISO_OK;
     ISO_REQUIRE(ctx, d_pars && d_lnpost, "lnpost: NULL buffer");
     ISO_REQUIRE(ctx, d_model_of_row || models->n_models == 1, "lnpost: several models staged but no model_of_row given");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     IsoDeviceGuard guard(ctx->device);
     return lnpost_launch(ctx, ctx->stream, model_pack, bc_pack, models, d_model_of_row, d_pars, N, d_lnpost, d_lnprior,
                          d_lnlike);

@@ -32,6 +32,7 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
 {
     ISO_REQUIRE(ctx, n_arrays >= 1 && n_arrays <= ISO_PIPE_MAX_ARRAYS, "pipeline: bad array count");
     if (n_rows <= 0) return ISO_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);   // one pipelined call at a time per context
     IsoDeviceGuard guard(ctx->device);
 
     static const int64_t chunk_rows = [] {

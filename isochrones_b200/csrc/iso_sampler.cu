@@ -214,6 +214,7 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     ISO_REQUIRE(ctx, s && n_steps >= 0 && thin >= 1, "iso_sampler_run: bad argument");
     ISO_REQUIRE(ctx, s->device == ctx->device, "iso_sampler_run: sampler belongs to another device");
     if (n_steps == 0) return ISO_OK;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     IsoDeviceGuard guard(ctx->device);
     IsoSamplerParams P;
     size_t smem = 0;

@@ -283,3 +283,33 @@ def test_star_catalog_compile(world):
     want = oracle.lnpost_catalog(oms, mor, pars, n_threads=8)
     _compare(got, want, ATOL_LNPOST)
     assert np.isfinite(want).mean() > 0.9
+
+
+def test_concurrent_host_threads_share_a_context(world):
+    """ctypes releases the GIL: several host threads may call into one context at once; calls serialise on the
+    context's mutex and every thread gets its own correct results."""
+    import threading
+
+    from isochrones_b200 import synthetic as syn
+
+    mod, om, truth = _model(world, "track", 1)
+    batches = [syn.posterior_like_batch("track", 300_000 + 1000 * t, truth, seed=40 + t) for t in range(4)]
+    want = [mod.lnpost_batch(b) for b in batches]
+    got = [None] * 4
+    errs = []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                got[t] = mod.lnpost_batch(batches[t])
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs
+    for t in range(4):
+        assert np.array_equal(got[t], want[t], equal_nan=True)
