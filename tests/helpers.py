@@ -230,3 +230,27 @@ def replay_stretch_move(lnpost_fn, p0, n_steps, seed, a=2.0, chain=0):
         out[s] = pos
         out_lp[s] = lp
     return out, out_lp, n_acc
+
+
+# ---------------------------------------------------------------------------
+# full-size benchmark grids + the reference's outputs on them (tests/golden/golden_full.npz)
+# ---------------------------------------------------------------------------
+
+def full_size_world():
+    """(meta, arrays, grids): grids regenerated by isochrones_b200.synthetic and verified bit for bit against the
+    SHA-256 digests recorded when oracle/make_golden_full.py ran the reference on them."""
+    import hashlib
+    import os
+
+    from isochrones_b200 import synthetic as syn
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "golden_full.npz"), allow_pickle=False)
+    meta = json.loads(str(g["meta_json"]))
+    trk = syn.make_track_grid(columns=tuple(meta["track_columns"]))
+    iso = syn.make_iso_grid(columns=tuple(meta["iso_columns"]))
+    bc = syn.make_bc_grid(bands=tuple(meta["bands"]))
+    for name, grid in (("track", trk), ("iso", iso), ("bc", bc)):
+        got = hashlib.sha256(np.ascontiguousarray(grid["grid"]).tobytes()).hexdigest()
+        assert got == meta[name + "_sha256"], "synthetic %s grid differs from the one the reference was run on" % name
+    return meta, g, {"track": trk, "iso": iso, "bc": bc}
