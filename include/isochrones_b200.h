@@ -102,6 +102,13 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
                     const double *h_pars, int64_t N, double *h_Teff, double *h_logg, double *h_feh,
                     double *h_mags);
 
+/* interp_eeps (interp.py:488-499) over interp_eep (:502-558): (age, feh, mass) -> EEP on an evolution-track grid
+ * staged as a 3-D (feh, mass, eep) iso_grid whose column i_age holds log10 age (the per-track age arrays of
+ * StellarModelGrid.get_array_grids, models.py:171-205); h_lengths[n_feh * n_mass] is the number of populated EEPs
+ * of every track.  NaN in / out of bounds / beyond the last tabulated EEP -> NaN. */
+int iso_interp_eeps(iso_ctx *ctx, const iso_grid *track_grid, int i_age, const int32_t *h_lengths, const double *h_age,
+                    const double *h_feh, const double *h_mass, int64_t N, double *h_eep);
+
 /* ------------------------------------------------------------------------------------------------
  * priors — replace the lnpdf / __call__ evaluation of priors.py
  * ---------------------------------------------------------------------------------------------- */

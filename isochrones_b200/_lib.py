@@ -90,6 +90,7 @@ SIGNATURES = {
     "iso_interp_values": (C.c_int, [_VP, _VP, C.POINTER(c_double_p), C.c_int64, c_int32_p, C.c_int, c_double_p]),
     "iso_interp_mags": (C.c_int, [_VP, _VP, _VP, c_int32_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, C.c_int,
                                   c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "iso_interp_eeps": (C.c_int, [_VP, _VP, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "iso_prior_eval": (C.c_int, [_VP, C.POINTER(IsoPrior), C.c_int, c_double_p, C.c_int64, c_double_p]),
     "iso_models_stage": (C.c_int, [_VP, C.POINTER(IsoModel), C.c_int, C.POINTER(_VP)]),
     "iso_models_destroy": (C.c_int, [_VP, _VP]),

@@ -116,6 +116,66 @@ iso_interp_mags_kernel(IsoGridDev model, IsoGridDev bc, IsoMagsArgs a)
     }
 }
 
+// interp_eeps (interp.py:488-499) over interp_eep (:502-558): (age, feh, mass) -> EEP on an evolution-track grid.
+// The per-track age arrays of the reference (StellarModelGrid.get_array_grids, models.py:171-205) are the `i_age`
+// column of the staged (feh, mass, eep) grid; lengths[t] is the number of leading populated EEPs of track t.
+struct IsoEepArgs {
+    const double *age, *feh, *mass;   // device [N]
+    const int *lengths;               // device [n_feh * n_mass]
+    double *out;                      // device [N]
+    long long N;
+    int i_age;
+};
+
+__global__ void __launch_bounds__(ISO_INTERP_THREADS) iso_interp_eeps_kernel(IsoGridDev g, IsoEepArgs a)
+{
+    const double nan = iso_nan();
+    const int n0 = g.n[0], n1 = g.n[1], n_eep = g.n[2];
+    const long long n_tracks = (long long)n0 * n1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+        const double x = a.age[i], x0 = a.feh[i], x1 = a.mass[i];
+        if (x != x || !iso_in_bounds(g.ax[0], x0) || !iso_in_bounds(g.ax[1], x1)) {   // NaN in / out of bounds -> NaN
+            a.out[i] = nan;
+            continue;
+        }
+        double d0, d1;
+        const int i0 = iso_axis_locate(g.ax[0], g.nodes + g.ax[0].off, x0, d0);
+        const int i1 = iso_axis_locate(g.ax[1], g.nodes + g.ax[1].off, x1, d1);
+        // the reference's unchecked track indices: 00, 01, 10, 11 (interp.py:515-518)
+        const long long ind[4] = {(long long)i0 * n1 + i1, (long long)i0 * n1 + (i1 + 1), (long long)(i0 + 1) * n1 + i1,
+                                  (long long)(i0 + 1) * n1 + (i1 + 1)};
+        double eep[4];
+        int ie[4], len[4];
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            len[k] = ind[k] < n_tracks ? a.lengths[ind[k]] : 0;   // a track beyond the array (weight 0) counts as empty
+            const double *arr = g.g + (size_t)ind[k] * n_eep * g.ncols + a.i_age;
+            int lo = 0, n = len[k];                               // searchsorted: number of ages < x (an exact hit returns its index)
+            while (n > 0) {
+                const int half = n >> 1;
+                const bool less = __ldg(arr + (size_t)(lo + half) * g.ncols) < x;
+                lo = less ? lo + half + 1 : lo;
+                n = less ? n - half - 1 : half;
+            }
+            ie[k] = lo;
+            bad = bad || (lo > n_eep - 1);                        // max_i_eep (interp.py:526-528)
+            eep[k] = (double)(lo + 1);                            // EEP = index + 1
+        }
+        if (bad) {
+            a.out[i] = nan;
+            continue;
+        }
+        if (ie[0] >= len[0]) eep[0] = eep[1];                     // sequential, as written (interp.py:540-551)
+        if (ie[1] >= len[1]) eep[1] = eep[0];
+        if (ie[2] >= len[2]) eep[2] = eep[3];
+        if (ie[3] >= len[3]) eep[3] = eep[2];
+        const double eep_0 = __dadd_rn(__dmul_rn(1.0 - d1, eep[0]), __dmul_rn(d1, eep[1]));
+        const double eep_1 = __dadd_rn(__dmul_rn(1.0 - d1, eep[2]), __dmul_rn(d1, eep[3]));
+        a.out[i] = __dadd_rn(__dmul_rn(1.0 - d0, eep_0), __dmul_rn(d0, eep_1));
+    }
+}
+
 static int grid_blocks(iso_ctx *ctx, int64_t n, int threads)
 {
     int64_t want = (n + threads - 1) / threads;
@@ -167,6 +227,31 @@ static int mags_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t ro
     a.N = n;
     int blocks = grid_blocks(ctx, n, ISO_INTERP_THREADS);
     iso_interp_mags_kernel<<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->model->dev, u->bc->dev, a);
+    ctx->launches++;
+    ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+struct EepUser {
+    const iso_grid *grid;
+    const int *d_lengths;
+    int i_age;
+};
+
+static int eep_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    (void)row0;
+    EepUser *u = (EepUser *)user;
+    IsoEepArgs a;
+    a.age = (const double *)d[0];
+    a.feh = (const double *)d[1];
+    a.mass = (const double *)d[2];
+    a.out = (double *)d[3];
+    a.lengths = u->d_lengths;
+    a.N = n;
+    a.i_age = u->i_age;
+    int blocks = grid_blocks(ctx, n, ISO_INTERP_THREADS);
+    iso_interp_eeps_kernel<<<blocks, ISO_INTERP_THREADS, 0, st>>>(u->grid->dev, a);
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());
     return ISO_OK;
@@ -250,6 +335,30 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
     u.proto.bc_cols = cols.d;
     u.proto.n_bands = n_bands;
     return iso_run_pipeline(ctx, N, arr, 9, mags_launch, &u);
+}
+
+int iso_interp_eeps(iso_ctx *ctx, const iso_grid *track_grid, int i_age, const int32_t *h_lengths, const double *h_age,
+                    const double *h_feh, const double *h_mass, int64_t N, double *h_eep)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_eeps: ctx is NULL");
+    ISO_REQUIRE(ctx, track_grid && h_lengths, "iso_interp_eeps: NULL argument");
+    ISO_REQUIRE(ctx, track_grid->device == ctx->device, "iso_interp_eeps: grid belongs to another device");
+    ISO_REQUIRE(ctx, track_grid->dev.ndim == 3, "iso_interp_eeps: needs a 3-D (feh, mass, eep) grid");
+    ISO_REQUIRE(ctx, i_age >= 0 && i_age < track_grid->dev.ncols, "iso_interp_eeps: age column out of range");
+    ISO_REQUIRE(ctx, N >= 0, "iso_interp_eeps: negative N");
+    const int n_tracks = track_grid->dev.n[0] * track_grid->dev.n[1];
+    for (int t = 0; t < n_tracks; t++)
+        ISO_REQUIRE(ctx, h_lengths[t] >= 0 && h_lengths[t] <= track_grid->dev.n[2], "iso_interp_eeps: bad track length");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_age && h_feh && h_mass && h_eep, "iso_interp_eeps: NULL buffer");
+    IsoDeviceGuard guard(ctx->device);
+    DevInts lengths;
+    int rc = lengths.upload(ctx, h_lengths, n_tracks);
+    if (rc != ISO_OK) return rc;
+    IsoPipeArray arr[4] = {IsoPipeArray{h_age, nullptr, 8}, IsoPipeArray{h_feh, nullptr, 8}, IsoPipeArray{h_mass, nullptr, 8},
+                           IsoPipeArray{nullptr, h_eep, 8}};
+    EepUser u{track_grid, lengths.d, i_age};
+    return iso_run_pipeline(ctx, N, arr, 4, eep_launch, &u);
 }
 
 }  // extern "C"

@@ -8,7 +8,8 @@ bands)`` (:402-445), ``initialize`` (:349-358) and the property shortcuts (``mas
 
 Out of scope: grid download / parsing (``Grid``, ``StellarModelGrid``, ``MIST*Grid``).  The grids
 come in as dense arrays — synthetic MIST-shaped ones from :mod:`isochrones_b200.synthetic`, or the reference's own
-cached ``.npz`` dense grids through :func:`isochrones_b200.loaders` — and are staged once to HBM.
+cached ``.npz`` dense grids through ``DFInterpolator.from_npz`` — and are staged once to HBM.  Also here (SURVEY.md
+§8f-3): ``get_eep`` (``interp_eep(s)``, interp.py:488-558) and ``generate`` (models.py:580-629) on the same kernels.
 """
 import ctypes as C
 
@@ -31,6 +32,32 @@ class ModelGrid(object):
 
     def get_limits(self, prop):
         return self._limits[prop]          # reference grid.py:58-61 / mist/models.py:37
+
+    def get_array_grids(self):
+        """``(age_grid[n_feh * n_mass, n_eep], dt_deep_grid, lengths)`` of an evolution-track grid — the irregular
+        per-track age arrays ``interp_eep`` searches (host-side data prep, models.py:171-205): the populated leading
+        run of every track's age / dt_deep column, NaN beyond it."""
+        if self.eep_replaces != "age":
+            raise NotImplementedError("Not implemented for isochrone grids yet!")
+        if getattr(self, "_array_grids", None) is None:
+            it = self.interp
+            g = it.grid
+            n_eep = g.shape[2]
+            age = g[..., it.column_index["age"]].reshape(-1, n_eep)
+            dt = g[..., it.column_index["dt_deep"]].reshape(-1, n_eep)
+            nan = np.isnan(age)
+            lengths = np.where(nan.any(axis=1), nan.argmax(axis=1), n_eep).astype(np.int64)
+            mask = np.arange(n_eep)[None, :] < lengths[:, None]
+            self._array_grids = (np.where(mask, age, np.nan), np.where(mask, dt, np.nan), lengths)
+        return self._array_grids
+
+    age_grid = property(lambda self: self.get_array_grids()[0])
+    dt_deep_grid = property(lambda self: self.get_array_grids()[1])
+    array_lengths = property(lambda self: self.get_array_grids()[2])
+
+    @property
+    def n_masses(self):
+        return len(self.masses)
 
     @property
     def fehs(self):
@@ -233,6 +260,61 @@ class ModelGridInterpolator(object):
         if scalar:
             return float(teff[0]), float(logg[0]), float(feh[0]), mags[0]
         return teff, logg, feh, mags
+
+    def get_eep(self, mass, age, feh, accurate=False, **kwargs):
+        """EEP of a star of given (mass, log10 age, feh) on an evolution-track grid (models.py:501-542): the fast
+        bracketing interpolation ``interp_eep(s)`` (interp.py:488-558) on the GPU (``iso_interp_eeps``).  Scalars give
+        a float, anything else is broadcast.  ``accurate=True`` (scipy minimisation, models.py:544-578) is outside the
+        accelerated path."""
+        if accurate:
+            raise NotImplementedError("get_eep(accurate=True) is a host-side scipy minimisation; not on the accelerated path")
+        if self.eep_replaces != "age":
+            raise NotImplementedError
+        scalar = all(isinstance(v, (float, int)) for v in (mass, age, feh))
+        b = np.broadcast(mass, age, feh)
+        age_a, feh_a, mass_a = [np.ascontiguousarray(np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel())
+                                for x in (age, feh, mass)]
+        lengths = np.ascontiguousarray(self.model_grid.array_lengths, dtype=np.int32)
+        out = np.empty(len(age_a))
+        ctx = self.ctx
+        ctx.check(_lib.lib().iso_interp_eeps(ctx.handle, self.model_pack.handle, 4, _lib.ip(lengths), _lib.dp(age_a),
+                                             _lib.dp(feh_a), _lib.dp(mass_a), len(age_a), _lib.dp(out)))
+        return float(out[0]) if scalar else out
+
+    def generate(self, mass, age, feh, props="all", bands=None, eeps=None, return_df=True, return_dict=False,
+                 distance=10, AV=0, all_As=False, **kwargs):
+        """Synthesise stars of given (mass, log10 age, feh): EEP lookup, all model-grid properties and apparent
+        magnitudes (models.py:580-629) — three kernel launches for the whole batch."""
+        import pandas as pd
+
+        mass, age, feh, distance, AV = [np.atleast_1d(a) if np.size(a) > 1 else float(a)
+                                        for a in np.broadcast_arrays(mass, age, feh, distance, AV)]
+        if bands is None:
+            bands = self.bands
+        if eeps is None:
+            eeps = self.get_eep(mass, age, feh, **kwargs)
+        cols = list(self.model_grid.interp.columns) if isinstance(props, str) and props == "all" else list(props)
+        values = self.interp_value([mass, eeps, feh], cols)
+        if bands:
+            _, _, _, mags = self.interp_mag([mass, eeps, feh, distance, AV], bands)
+            axis = 1 if values.ndim == 2 else 0
+            values = np.concatenate([values, mags], axis=axis)
+        names = cols + ["{}_mag".format(b) for b in bands]
+        if return_dict:
+            values = dict(zip(names, values.T if values.ndim == 2 else values))
+        elif return_df:
+            values = pd.DataFrame(np.atleast_2d(values), columns=names)
+        else:
+            return values
+        values["distance"] = distance
+        values["AV"] = AV
+        values["initial_feh"] = feh
+        values["requested_age"] = age
+        if all_As:
+            _, _, _, true_mags = self.interp_mag([mass, eeps, feh, distance, 0.0], bands)
+            for b, true_mag in zip(bands, np.atleast_2d(true_mags).T):
+                values["A_{}".format(b)] = values["{}_mag".format(b)] - true_mag
+        return values
 
     def __call__(self, p1, p2, p3, distance=10.0, AV=0.0):
         """All model-grid columns + magnitudes as a DataFrame (models.py:471-482) — same kernels, wider output."""

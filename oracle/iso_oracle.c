@@ -169,6 +169,57 @@ void orc_interp_mags(const double *pars, int64_t N, const int32_t *index_order, 
     }
 }
 
+/* interp.py:502-558 interp_eep (+ :488-499 interp_eeps): (age x, feh x0, mass x1) -> EEP on an evolution-track grid.
+ * find_indices_2d (interp.py:63-93) brackets (feh, mass); searchsorted (interp.py:10-35) over the first lengths[t]
+ * ages of each of the four bracketing tracks gives the EEP index (EEP = index + 1); a track that ends before x
+ * borrows its mass-neighbour's EEP; the four EEPs are blended bilinearly.  `arrays` is [n0 * n1, n_eep].
+ * The reference indexes tracks i0 * n1 + (i1 + 1) and (i0 + 1) * n1 + .. without bounds checks; a track index beyond
+ * the array (weight always 0 there) is treated as an empty track. */
+double orc_interp_eep(double x, double x0, double x1, const double *ii0, int64_t n0, const double *ii1, int64_t n1,
+                      const double *arrays, int64_t n_eep, const int64_t *lengths)
+{
+    int64_t i0, i1, ind[4], i_eep[4], len[4], n_tracks = n0 * n1;
+    double d0, d1, eep[4], eep_0, eep_1;
+    int32_t eq;
+    int k;
+    if (x != x || x0 != x0 || x1 != x1) return NAN;
+    if (x0 < ii0[0] || x0 > ii0[n0 - 1] || x1 < ii1[0] || x1 > ii1[n1 - 1]) return NAN;
+    i0 = orc_searchsorted(ii0, n0, x0, &eq);
+    if (eq) d0 = 0; else { i0 -= 1; d0 = (x0 - ii0[i0]) / (ii0[i0 + 1] - ii0[i0]); }
+    i1 = orc_searchsorted(ii1, n1, x1, &eq);
+    if (eq) d1 = 0; else { i1 -= 1; d1 = (x1 - ii1[i1]) / (ii1[i1 + 1] - ii1[i1]); }
+    ind[0] = i0 * n1 + i1;            /* 00 */
+    ind[1] = i0 * n1 + (i1 + 1);      /* 01 */
+    ind[2] = (i0 + 1) * n1 + i1;      /* 10 */
+    ind[3] = (i0 + 1) * n1 + (i1 + 1);/* 11 */
+    for (k = 0; k < 4; k++) {
+        if (ind[k] < n_tracks && lengths[ind[k]] > 0) {
+            len[k] = lengths[ind[k]];
+            i_eep[k] = orc_searchsorted(arrays + ind[k] * n_eep, len[k], x, &eq);
+        } else {
+            len[k] = 0;
+            i_eep[k] = 0;
+        }
+        if (i_eep[k] > n_eep - 1) return NAN;   /* max_i_eep = weight_arrays.shape[1] - 1 */
+        eep[k] = (double)(i_eep[k] + 1);
+    }
+    if (i_eep[0] >= len[0]) eep[0] = eep[1];   /* sequential, as written in the reference */
+    if (i_eep[1] >= len[1]) eep[1] = eep[0];
+    if (i_eep[2] >= len[2]) eep[2] = eep[3];
+    if (i_eep[3] >= len[3]) eep[3] = eep[2];
+    eep_0 = (1 - d1) * eep[0] + d1 * eep[1];
+    eep_1 = (1 - d1) * eep[2] + d1 * eep[3];
+    return (1 - d0) * eep_0 + d0 * eep_1;
+}
+
+void orc_interp_eeps(const double *xs, const double *x0s, const double *x1s, int64_t N, const double *ii0, int64_t n0,
+                     const double *ii1, int64_t n1, const double *arrays, int64_t n_eep, const int64_t *lengths,
+                     double *out)
+{
+    int64_t i;
+    for (i = 0; i < N; i++) out[i] = orc_interp_eep(xs[i], x0s[i], x1s[i], ii0, n0, ii1, n1, arrays, n_eep, lengths);
+}
+
 /* likelihood.py:10-13 — note the + log(unc) */
 double orc_gauss_lnprob(double val, double unc, double model_val)
 {

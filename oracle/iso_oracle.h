@@ -98,6 +98,11 @@ void orc_interp_mags(const double *pars, int64_t N, const int32_t *index_order, 
                      int32_t i_Teff, int32_t i_logg, int32_t i_feh, int32_t i_Mbol, const orc_grid *bc,
                      const int32_t *bc_cols, int32_t n_bands, double *Teffs, double *loggs, double *fehs,
                      double *mags);
+double orc_interp_eep(double x, double x0, double x1, const double *ii0, int64_t n0, const double *ii1, int64_t n1,
+                      const double *arrays, int64_t n_eep, const int64_t *lengths);
+void orc_interp_eeps(const double *xs, const double *x0s, const double *x1s, int64_t N, const double *ii0, int64_t n0,
+                     const double *ii1, int64_t n1, const double *arrays, int64_t n_eep, const int64_t *lengths,
+                     double *out);
 double orc_gauss_lnprob(double val, double unc, double model_val);
 double orc_fast_addmags(const double *mags, int32_t n);
 double orc_prior_call(const orc_prior *p, double x);

@@ -362,11 +362,63 @@ def golden_priors(ref, out):
     out["pr_specs_json"] = np.array(json.dumps(specs))
 
 
+
+def track_age_arrays(trk):
+    """(arrays[n_feh * n_mass, n_eep], weight_arrays, lengths) as StellarModelGrid.get_array_grids builds them
+    (models.py:171-205): the leading non-NaN run of each track's age / dt_deep column."""
+    g = trk["grid"]
+    cols = trk["columns"]
+    age = g[..., cols.index("age")].reshape(-1, g.shape[2])
+    dt = g[..., cols.index("dt_deep")].reshape(-1, g.shape[2])
+    lengths = np.array([int(np.argmax(np.isnan(a))) if np.isnan(a).any() else len(a) for a in age], dtype=np.int64)
+    arrays = np.full_like(age, np.nan)
+    weights = np.full_like(dt, np.nan)
+    for i, n in enumerate(lengths):
+        arrays[i, :n] = age[i, :n]
+        weights[i, :n] = dt[i, :n]
+    return arrays, weights, lengths
+
+
+def golden_eep(ref, out):
+    """interp_eeps (interp.py:488-558): (age, feh, mass) -> EEP on the small and on a mid-size track grid."""
+    for tag, trk in (("small", grids_small()[0]), ("mid", syn.make_track_grid(n_feh=7, n_mass=40, n_eep=342))):
+        fehs, masses, eeps = trk["axes"]
+        arrays, weights, lengths = track_age_arrays(trk)
+        rng = np.random.RandomState(71)
+        n = 1500
+        x0 = fehs[0] + (fehs[-1] - fehs[0]) * rng.random_sample(n)
+        x1 = np.exp(np.log(masses[0]) + (np.log(masses[-1]) - np.log(masses[0])) * rng.random_sample(n))
+        x = 5.0 + 5.6 * rng.random_sample(n)
+        q = n // 5
+        x0[:q] = rng.choice(fehs[:-1], q)                 # exact [Fe/H] nodes (not the last: reference UB)
+        x1[q:2 * q] = rng.choice(masses, q)               # exact mass nodes, the last one included (flat-offset read)
+        x[2 * q:3 * q] = arrays[rng.randint(0, len(arrays), q), rng.randint(0, 5, q)]   # exact ages of some track
+        x1[3 * q:3 * q + 20] = masses[-1] + 1.0           # out of bounds
+        x0[3 * q + 20:3 * q + 40] = fehs[0] - 0.1
+        x[3 * q + 40:3 * q + 60] = np.nan
+        x0[x0 >= fehs[-1]] = fehs[-2]
+        # mass on its last node makes the reference read track (i0 + 1) * n1 + n1: beyond the array in the last [Fe/H] cell
+        x0[(x1 >= masses[-1]) & (x0 >= fehs[-2])] = fehs[0] + 0.3 * (fehs[1] - fehs[0])
+        res = ref.interp.interp_eeps(x, x0, x1, fehs, masses, len(masses), arrays, weights, lengths)
+        one = np.array([ref.interp.interp_eep(float(a), float(b), float(c), fehs, masses, len(masses), arrays, weights, lengths)
+                        for a, b, c in zip(x[:16], x0[:16], x1[:16])])
+        assert np.array_equal(one, res[:16], equal_nan=True)
+        out[tag + "_age"], out[tag + "_feh"], out[tag + "_mass"], out[tag + "_eep"] = x, x0, x1, res
+        out[tag + "_lengths"] = lengths
+        if tag == "small":
+            pack_grid("trk", trk, out)
+        else:
+            out["mid_shape"] = np.array([7, 40, 342])
+        print("eep", tag, "finite", int(np.isfinite(res).sum()), "nan", int(np.isnan(res).sum()))
 def main():
     ref = ref_shim.load()
+
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
     for name, fn in (("interp", golden_interp), ("mags", golden_mags), ("lnpost", golden_lnpost),
-                     ("priors", golden_priors)):
+                     ("priors", golden_priors), ("eep", golden_eep)):
+        if only and name not in only:
+            continue
         out = {}
         fn(ref, out)
         path = os.path.join(OUT, "golden_%s.npz" % name)

@@ -93,6 +93,9 @@ def lib():
         L.orc_interp_mags.argtypes = [c_double_p, C.c_int64, c_int32_p, C.POINTER(OrcGrid), C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.POINTER(OrcGrid), c_int32_p, C.c_int32,
                                       c_double_p, c_double_p, c_double_p, c_double_p]
+        L.orc_interp_eeps.restype = None
+        L.orc_interp_eeps.argtypes = [c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p,
+                                      C.c_int64, c_double_p, C.c_int64, C.POINTER(C.c_int64), c_double_p]
         for name in ("orc_gauss_lnprob",):
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_double] * 3
@@ -176,6 +179,19 @@ def interp_mags(pars, index_order, model, i_Teff, i_logg, i_feh, i_Mbol, bc, bc_
     lib().orc_interp_mags(_dp(pars), n, _ip(io), C.byref(model.struct), i_Teff, i_logg, i_feh, i_Mbol,
                           C.byref(bc.struct), _ip(bc_cols), len(bc_cols), _dp(teff), _dp(logg), _dp(feh), _dp(mags))
     return teff, logg, feh, mags
+
+
+def interp_eeps(xs, x0s, x1s, ii0, ii1, arrays, lengths):
+    """interp.py:488-558 — (age, feh, mass) -> EEP; ``arrays`` is ``[len(ii0) * len(ii1), n_eep]``."""
+    xs, x0s, x1s = [np.ascontiguousarray(a, dtype=np.float64) for a in (xs, x0s, x1s)]
+    ii0, ii1 = np.ascontiguousarray(ii0, dtype=np.float64), np.ascontiguousarray(ii1, dtype=np.float64)
+    arrays = np.ascontiguousarray(arrays, dtype=np.float64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    assert arrays.shape[0] == len(ii0) * len(ii1) == len(lengths)
+    out = np.empty(len(xs))
+    lib().orc_interp_eeps(_dp(xs), _dp(x0s), _dp(x1s), len(xs), _dp(ii0), len(ii0), _dp(ii1), len(ii1), _dp(arrays),
+                          arrays.shape[1], lengths.ctypes.data_as(C.POINTER(C.c_int64)), _dp(out))
+    return out
 
 
 _KINDS = {
