@@ -436,6 +436,7 @@ def main():
 
     from isochrones_b200 import _lib, parallel, synthetic as syn
 
+    numa_cpus = parallel.bind_to_gpu_numa(local_rank) if world > 1 else None   # before any pinned allocation
     ctx = _lib.default_context(local_rank)
     trk, bc, ic, truth, n_eep = build_workload(ctx=ctx, small=args.small)
     mags, mg, bg = truth_mags(trk, bc, truth)
@@ -573,7 +574,8 @@ def main():
                    "batch_rows": BATCH, "rows_per_gpu_per_step": BATCH, "distribution": "posterior-like (sigma: mass .05, "
                    "eep 15, feh .1, d 2 pc, AV .05)", "l2": "inputs larger than L2: steps rotate over %d distinct 1e6-row "
                    "batches (%d MB)" % (N_BATCHES, N_BATCHES * BATCH * 40 // 2 ** 20), "finite_frac": finite_frac,
-                   "sharding": "rows sharded across ranks, no data-path collective" if world > 1 else "single GPU"},
+                   "sharding": "rows sharded across ranks, no data-path collective" if world > 1 else "single GPU",
+                   "host_numa_binding": ("rank 0 bound to %d GPU-local cores" % len(numa_cpus)) if numa_cpus else "none"},
         "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 40, "d2h_bytes_per_step": BATCH * 8,
                 "api": "BasicStarModel.lnpost_batch(pinned host array) -> iso_lnpost_batch (C ABI), chunked "

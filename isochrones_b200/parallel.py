@@ -18,6 +18,35 @@ import numpy as np
 from . import _lib
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU (its NUMA node) so that pinned host buffers
+    allocated afterwards are first-touched on that node: with one process per GPU on a multi-socket box, host<->device
+    DMA then stays off the inter-socket link.  Returns the CPU list, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if vis:
+            try:
+                idx = int(vis.split(",")[device_index])
+            except (ValueError, IndexError):
+                idx = device_index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = {i for i in range(n_cpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        cpus = sorted(local & allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class RowSharder(object):
     """Contiguous, balanced row blocks: rank r owns rows [start(r), stop(r)); the first ``n % world`` ranks hold one
     extra row.  Gathers are padded to ``pad`` rows per rank so that one fixed-size all-gather serves every rank."""
