@@ -409,9 +409,10 @@ class EEP_prior(BoundedPrior):
             return [kwargs["mass"], eep, kwargs["feh"]]
         return [eep, kwargs["age"], kwargs["feh"]]
 
-    def pdf(self, eep, **kwargs):
+    def pdf(self, x, **kwargs):
         """Prior.pdf (priors.py:54-59) over EEP_prior._pdf (:423-429); grid interpolation and the original
         prior both run on the GPU.  Scalars or equal-length arrays."""
+        eep = x
         scalar = all(_is_scalar(v) for v in [eep] + list(kwargs.values()))
         pars = [np.atleast_1d(np.asarray(v, dtype=float)) for v in self._pars(eep, kwargs)]
         vals = np.atleast_2d(self.ic.interp_value(pars, [self.orig_par, self.deriv_prop]))
@@ -424,11 +425,11 @@ class EEP_prior(BoundedPrior):
                 pdf = np.where((e < lo) | (e > hi), 0.0, pdf)
         return float(pdf[0]) if scalar else pdf
 
-    def __call__(self, eep, **kwargs):
-        return self.pdf(eep, **kwargs)
+    def __call__(self, x, **kwargs):
+        return self.pdf(x, **kwargs)
 
-    def lnpdf(self, eep, **kwargs):
-        pdf = self.pdf(eep, **kwargs)
+    def lnpdf(self, x, **kwargs):
+        pdf = self.pdf(x, **kwargs)
         with np.errstate(divide="ignore", invalid="ignore"):
             out = np.where(np.asarray(pdf) == 0, -np.inf, np.log(np.where(np.asarray(pdf) == 0, 1.0, pdf)))
         return float(out) if _is_scalar(pdf) else out
