@@ -5,11 +5,43 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+
 #include "iso_common.cuh"
 
 #define ISO_PIPE_CHUNK_ROWS (1 << 18)
+#ifndef ISO_PIPE_PAGEABLE_DEFAULT
+#define ISO_PIPE_PAGEABLE_DEFAULT 0
+#endif
+#define ISO_PIPE_REGISTER_MIN_BYTES (4 << 20)
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+// host copy into / out of the pinned staging buffers, split over a few threads (one core moves ~12 GB/s, PCIe 57)
+static void staged_memcpy(void *dst, const void *src, size_t bytes)
+{
+    static const unsigned n_threads = [] {
+        const char *e = getenv("ISO_PIPE_COPY_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned v = e ? (unsigned)atoi(e) : (hw >= 8 ? 4u : 1u);
+        return v < 1 ? 1u : (v > 16 ? 16u : v);
+    }();
+    if (n_threads == 1 || bytes < ((size_t)1 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes / n_threads) + 4095) & ~(size_t)4095;
+    std::thread workers[16];
+    unsigned used = 0;
+    for (unsigned t = 1; t < n_threads; t++) {
+        const size_t a = (size_t)t * slice;
+        if (a >= bytes) break;
+        const size_t n = a + slice < bytes ? slice : bytes - a;
+        workers[used++] = std::thread([=] { memcpy((char *)dst + a, (const char *)src + a, n); });
+    }
+    memcpy(dst, src, slice < bytes ? slice : bytes);
+    for (unsigned t = 0; t < used; t++) workers[t].join();
+}
 
 static bool is_pinned(const void *p)
 {
@@ -40,19 +72,49 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         long long v = e ? atoll(e) : 0;
         return (int64_t)(v >= 1024 ? v : ISO_PIPE_CHUNK_ROWS);
     }();
+    // how caller buffers that are NOT page-locked travel: 0 = copy through the context's pinned staging buffers,
+    // 1 = hand the pageable pointer to cudaMemcpyAsync (the driver stages it), 2 = page-lock the caller's array for the
+    // duration of the call (cudaHostRegister) and DMA it directly
+    static const int pageable_mode = [] {
+        const char *e = getenv("ISO_PIPE_PAGEABLE");
+        return e ? atoi(e) : ISO_PIPE_PAGEABLE_DEFAULT;
+    }();
     int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
     int64_t off[ISO_PIPE_MAX_ARRAYS + 1];
     bool pinned[ISO_PIPE_MAX_ARRAYS];
     bool active[ISO_PIPE_MAX_ARRAYS];
     off[0] = 0;
     bool any_pageable = false;
+    void *registered[ISO_PIPE_MAX_ARRAYS];
     for (int k = 0; k < n_arrays; k++) {
         const void *h = arrays[k].h_in ? arrays[k].h_in : arrays[k].h_out;
         active[k] = (h != nullptr);
         pinned[k] = active[k] && is_pinned(h);
+        registered[k] = nullptr;
+        if (active[k] && !pinned[k]) {
+            const size_t bytes = (size_t)(n_rows * arrays[k].row_bytes);
+            if (pageable_mode == 1) {
+                pinned[k] = true;   // treated like a pinned pointer: the driver stages pageable memory itself
+            } else if (pageable_mode == 2 && bytes >= ISO_PIPE_REGISTER_MIN_BYTES &&
+                       cudaHostRegister(const_cast<void *>(h), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                registered[k] = const_cast<void *>(h);
+                pinned[k] = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
         if (active[k] && !pinned[k]) any_pageable = true;
         off[k + 1] = off[k] + (active[k] ? align256(chunk * arrays[k].row_bytes) : 0);
     }
+    struct Unregister {
+        void **r;
+        int n;
+        ~Unregister()
+        {
+            for (int k = 0; k < n; k++)
+                if (r[k]) cudaHostUnregister(r[k]);
+        }
+    } unregister{registered, n_arrays};
     int n_slots = n_rows > chunk ? 2 : 1;
     for (int s = 0; s < n_slots; s++) {
         int rc = iso_stage_reserve(ctx, s, off[n_arrays], any_pageable ? off[n_arrays] : 0);
@@ -68,8 +130,8 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         ISO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[s]));
         for (int k = 0; k < n_arrays; k++) {
             if (!active[k] || pinned[k] || !arrays[k].h_out) continue;
-            memcpy((char *)arrays[k].h_out + slots[s].row0 * arrays[k].row_bytes, (char *)ctx->h_stage[s] + off[k],
-                   (size_t)(slots[s].n * arrays[k].row_bytes));
+            staged_memcpy((char *)arrays[k].h_out + slots[s].row0 * arrays[k].row_bytes, (char *)ctx->h_stage[s] + off[k],
+                          (size_t)(slots[s].n * arrays[k].row_bytes));
         }
         slots[s].busy = false;
         return ISO_OK;
@@ -89,7 +151,7 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
             const char *src = (const char *)arrays[k].h_in + row0 * arrays[k].row_bytes;
             size_t bytes = (size_t)(n * arrays[k].row_bytes);
             if (!pinned[k]) {
-                memcpy((char *)ctx->h_stage[s] + off[k], src, bytes);
+                staged_memcpy((char *)ctx->h_stage[s] + off[k], src, bytes);
                 src = (const char *)ctx->h_stage[s] + off[k];
             }
             ISO_CUDA(ctx, cudaMemcpyAsync(d_arrays[k], src, bytes, cudaMemcpyHostToDevice, st));
