@@ -267,7 +267,11 @@ class ModelGridInterpolator(object):
         a float, anything else is broadcast.  ``accurate=True`` (scipy minimisation, models.py:544-578) is outside the
         accelerated path."""
         if accurate:
-            raise NotImplementedError("get_eep(accurate=True) is a host-side scipy minimisation; not on the accelerated path")
+            b = np.broadcast(mass, age, feh)
+            if b.shape == ():
+                return self.get_eep_accurate(float(mass), float(age), float(feh), **kwargs)
+            pars = [np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel() for x in (mass, age, feh)]
+            return np.array([self.get_eep_accurate(m, a, f, **kwargs) for m, a, f in zip(*pars)])
         if self.eep_replaces != "age":
             raise NotImplementedError
         scalar = all(isinstance(v, (float, int)) for v in (mass, age, feh))
@@ -280,6 +284,55 @@ class ModelGridInterpolator(object):
         ctx.check(_lib.lib().iso_interp_eeps(ctx.handle, self.model_pack.handle, 4, _lib.ip(lengths), _lib.dp(age_a),
                                              _lib.dp(feh_a), _lib.dp(mass_a), len(age_a), _lib.dp(out)))
         return float(out[0]) if scalar else out
+
+    def max_eep(self, mass, feh):
+        """Last populated EEP of the track nearest below (mass, feh) (the reference asks the MIST table,
+        mist/utils.py:16-59; here it is read off the staged grid's NaN tails)."""
+        if self.eep_replaces != "age":
+            raise NotImplementedError
+        g = self.model_grid
+        i_f = max(0, int(np.searchsorted(g.fehs, feh, side="right")) - 1)
+        i_m = max(0, int(np.searchsorted(g.masses, mass, side="right")) - 1)
+        return int(g.array_lengths[i_f * len(g.masses) + i_m])
+
+    def mass_age_resid(self, eep, mass, age, feh):
+        """Squared residual the accurate EEP search minimises (models.py:678-682, 706-710) — one GPU interpolation."""
+        eep = float(np.squeeze(eep))
+        if self.eep_replaces == "age":
+            return float((age - self.interp_value([float(mass), eep, float(feh)], ["age"])[0]) ** 2)
+        return float((mass - self.interp_value([eep, float(age), float(feh)], ["initial_mass"])[0]) ** 2)
+
+    def get_eep_accurate(self, mass, age, feh, eep0=300, resid_tol=0.02, method="nelder-mead", return_object=False,
+                         return_nan=False, **kwargs):
+        """models.py:544-578: scipy minimisation of ``mass_age_resid`` (the optimiser loop stays on the host as in
+        the reference; every residual evaluation is a GPU interpolation)."""
+        from scipy.optimize import minimize
+
+        top = (self.max_eep(mass, feh) if self.eep_replaces == "age" else self.eep_bounds[1]) - 20
+        eeps_to_try = [min(top, 600), 100, 200]
+        while np.isnan(self.mass_age_resid(eep0, mass, age, feh)):
+            try:
+                eep0 = eeps_to_try.pop()
+            except IndexError:
+                if return_nan:
+                    return np.nan
+                raise ValueError("eep0 gives nan for all initial guesses! {}".format((mass, age, feh)))
+        result = minimize(self.mass_age_resid, eep0, args=(mass, age, feh), method=method, options=kwargs)
+        if return_object:
+            return result
+        if result.success and result.fun < resid_tol ** 2:
+            return float(np.squeeze(result.x))
+        if return_nan:
+            return np.nan
+        raise RuntimeError("EEP minimization not successful: {}".format((mass, age, feh)))
+
+    def isochrone(self, age, feh=0.0, eep_range=None, distance=10.0, AV=0.0, dropna=True):
+        """All properties along an isochrone / track section (models.py:484-493) — two kernel launches."""
+        if eep_range is None:
+            eep_range = self.model_grid.get_limits("eep")
+        eeps = np.arange(*eep_range)
+        df = self(eeps, age, feh, distance=distance, AV=AV)
+        return df.dropna() if dropna else df
 
     def generate(self, mass, age, feh, props="all", bands=None, eeps=None, return_df=True, return_dict=False,
                  distance=10, AV=0, all_As=False, **kwargs):
