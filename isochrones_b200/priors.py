@@ -120,6 +120,18 @@ class Prior(object):
             return self.distribution.rvs(n)
         raise NotImplementedError
 
+    def test_sampling(self, n=100000, plot=False):
+        """Histogram of ``sample(n)`` against bin-averaged pdf, within 6 sigma (priors.py:77-104; host-side check)."""
+        x = self.sample(n)
+        rng = None if tuple(self.bounds) == (-np.inf, np.inf) else self.bounds
+        hn, _ = np.histogram(x, range=rng)
+        h, b = np.histogram(x, density=True, range=rng)
+        pdf = np.array([quad(self._host_call, lo, hi)[0] / (hi - lo) for lo, hi in zip(b[:-1], b[1:])])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sigma = 1.0 / np.sqrt(hn)
+            resid = np.absolute(pdf - h) / pdf
+            assert max((resid / sigma)[hn > 50]) < 6
+
 
 class BoundedPrior(Prior):
     """priors.py:107-140: ``-inf`` / 0 outside ``bounds``."""
