@@ -9,7 +9,9 @@
 // interp_mag) and a third time for asteroseismology.
 #include "iso_lnpost_row.cuh"
 
+#ifndef ISO_LNPOST_THREADS
 #define ISO_LNPOST_THREADS 256
+#endif
 #ifndef ISO_LNPOST_MIN_BLOCKS
 #define ISO_LNPOST_MIN_BLOCKS 2
 #endif

@@ -33,6 +33,10 @@ def main():
         "prior": lambda s: syn.prior_like_batch("track", n, bounds, seed=3 + s),
         "scattered": lambda s: bench.scattered_batch(n, seed=50 + s),
         "grid_wide": lambda s: bench.grid_wide_batch(n, trk, seed=90 + s),
+        # bound experiments: every row identical (all gathers broadcast: the L1 data pipe costs nothing) and rows
+        # sharing one cell (distinct weights, same 24 nodes)
+        "identical": lambda s: np.tile(truth, (n, 1)),
+        "one_cell": lambda s: truth + np.array([0.004, 0.4, 0.01, 2.0, 0.02]) * np.random.RandomState(s).random_sample((n, 5)),
     }
     d_out = ctx.dev_alloc(n * 8)
     res = {}
