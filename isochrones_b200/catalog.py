@@ -20,40 +20,34 @@ from .starmodel import BinaryStarModel, CompiledModel, SingleStarModel, TripleSt
 class StarCatalog(object):
     def __init__(self, df, bands=None, props=None, no_uncs=False):
         self._df = df
-        if bands is None:
-            bands = []
-            for c in df.columns:
-                m = re.search("(.+)_mag$", c)
-                if m:
-                    bands.append(m.group(1))
+        if bands is None:      # every "<band>_mag" column names a band
+            bands = [m.group(1) for m in (re.fullmatch("(.+)_mag", str(c)) for c in df.columns) if m]
         self.bands = tuple(bands)
-        self.band_cols = tuple("{}_mag".format(b) for b in self.bands)
-        self.props = tuple() if props is None else tuple(props)
+        self.band_cols = tuple(b + "_mag" for b in self.bands)
+        self.props = tuple(props or ())
         if not no_uncs:
-            for c in self.band_cols + self.props:
-                if c not in self.df.columns:
-                    raise ValueError("{} not in DataFrame!".format(c))
-                if not "{}_unc".format(c) in self.df.columns:
-                    raise ValueError("{0} uncertainty ({0}_unc) not in DataFrame!".format(c))
+            missing = [c for c in self.band_cols + self.props if c not in df.columns]
+            if missing:
+                raise ValueError("{} not in DataFrame!".format(missing[0]))
+            no_unc = [c for c in self.band_cols + self.props if c + "_unc" not in df.columns]
+            if no_unc:
+                raise ValueError("{0} uncertainty ({0}_unc) not in DataFrame!".format(no_unc[0]))
         self._prior_settings = {}
 
-    def __len__(self):
-        return len(self.df)
+    df = property(lambda self: self._df)
 
-    @property
-    def df(self):
-        return self._df
+    def __len__(self):
+        return len(self._df)
 
     def get_measurement(self, prop, values=False):
-        return self.df[prop].values, self.df[prop + "_unc"].values
+        """``(values, uncertainties)`` of one measured quantity over the whole table."""
+        return self._df[prop].values, self._df[prop + "_unc"].values
 
     def iter_bands(self, **kwargs):
-        for b, col in zip(self.bands, self.band_cols):
-            yield b, self.get_measurement(col, **kwargs)
+        return ((b, self.get_measurement(c, **kwargs)) for b, c in zip(self.bands, self.band_cols))
 
     def iter_props(self, **kwargs):
-        for p in self.props:
-            yield p, self.get_measurement(p, **kwargs)
+        return ((p, self.get_measurement(p, **kwargs)) for p in self.props)
 
     def set_prior(self, **kwargs):
         """Prior settings applied to every model (catalog.py:116-124)."""

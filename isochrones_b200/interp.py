@@ -7,7 +7,6 @@ returns a 1-D array of ``len(cols)`` values, anything else is broadcast and retu
 (interp.py:631-698).  ``NaN`` means "outside the grid".  The dense grid is staged once to HBM on first use;
 each call is one CUDA launch (``iso_interp_values`` replaces ``interp_value(s)_{2,3,4}d``).
 """
-import itertools
 import os
 
 import numpy as np
@@ -63,26 +62,22 @@ class DFInterpolator(object):
         return cls.from_arrays(grid, index_columns, columns, index_names=index_names, ctx=ctx)
 
     def _make_grid(self, df, recalc=False):
-        # host-side, one-time data preparation (interp.py:590-614): NaN-pad a non-full index to a dense array
-        if self.filename is not None and os.path.exists(self.filename) and not recalc:
-            d = np.load(self.filename)
-            grid = d["grid"]
-            columns = d["columns"]
+        """Dense ``[n0, .., n_{d-1}, ncols]`` float64 array of a MultiIndex frame; index combinations the frame does
+        not hold stay NaN.  Host-side, one-time data preparation (the reference's interp.py:590-614); a ``filename``
+        caches the array in the reference's ``.npz`` layout (keys ``grid``, ``columns``)."""
+        cached = self.filename is not None and os.path.exists(self.filename) and not recalc
+        if cached:
+            with np.load(self.filename) as d:
+                grid, columns = d["grid"], d["columns"]
             if not all(columns == self.columns):
                 raise ValueError("DataFrame columns do not match columns loaded from full grid!")
-        else:
-            import pandas as pd
-
-            if not self.is_full:
-                idx = pd.MultiIndex.from_tuples([ixs for ixs in itertools.product(*df.index.levels)])
-                grid_df = pd.DataFrame(index=idx, columns=df.columns, dtype=float)
-                grid_df.loc[df.index] = df
-            else:
-                grid_df = df
-            shape = [len(l) for l in df.index.levels] + [len(df.columns)]
-            grid = np.array(grid_df.values, dtype=float).reshape(shape)
-            if self.filename is not None:
-                np.savez(self.filename, grid=grid, columns=self.columns)
+            return grid
+        levels_shape = tuple(len(level) for level in df.index.levels)
+        grid = np.full(levels_shape + (len(df.columns),), np.nan)
+        # scatter the rows through the index codes: no reindexing of the frame, works for full and ragged grids alike
+        grid[tuple(np.asarray(c) for c in df.index.codes)] = np.asarray(df.values, dtype=float)
+        if self.filename is not None:
+            np.savez(self.filename, grid=grid, columns=self.columns)
         return grid
 
     # ---- device residency -------------------------------------------------------------------------------
@@ -100,13 +95,12 @@ class DFInterpolator(object):
         return self._device_grid
 
     def add_column(self, values, name):
-        newgrid = np.empty((self.grid.shape[:-1]) + (self.n_columns + 1,))
-        newgrid[..., :-1] = self.grid
-        newgrid[..., -1] = values
+        """Append one column (``values`` broadcastable to the grid's node shape); drops the staged device copy."""
+        extra = np.broadcast_to(np.asarray(values, dtype=float), self.grid.shape[:-1])[..., None]
+        self.grid = np.concatenate([self.grid, extra], axis=-1)
+        self.columns = self.columns + [name]
         self.column_index[name] = self.n_columns
-        self.n_columns += 1
-        self.columns += [name]
-        self.grid = newgrid
+        self.n_columns = len(self.columns)
         self._device_grid = None
 
     def __call__(self, p, cols="all"):

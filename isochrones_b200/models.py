@@ -136,44 +136,12 @@ class ModelGridInterpolator(object):
         return self.model_grid.fehs
 
     def initialize(self, pars=None):
+        """Touch both grids once (stages them in HBM) and check that a typical star is inside them."""
         if pars is None:
-            if self.eep_replaces == "age":
-                pars = [1.04, 320.0, -0.35, 10000.0, 0.34]
-            elif self.eep_replaces == "mass":
-                pars = [320, 9.7, -0.35, 10000.0, 0.34]
+            pars = {"age": [1.04, 320.0, -0.35, 10000.0, 0.34], "mass": [320, 9.7, -0.35, 10000.0, 0.34]}[self.eep_replaces]
         Teff, logg, feh, mags = self.interp_mag(pars, self.bands)
-        assert all([np.isfinite(v) for v in [Teff, logg, feh]])
-        assert all([np.isfinite(m) for m in mags])
-
-    def _prop(self, prop, *pars):
-        return self.interp_value(pars, [prop]).squeeze()
-
-    def mass(self, *pars):
-        return self._prop("mass", *pars)
-
-    def initial_mass(self, *pars):
-        return self._prop("initial_mass", *pars)
-
-    def radius(self, *pars):
-        return self._prop("radius", *pars)
-
-    def Teff(self, *pars):
-        return self._prop("Teff", *pars)
-
-    def logg(self, *pars):
-        return self._prop("logg", *pars)
-
-    def feh(self, *pars):
-        return self._prop("feh", *pars)
-
-    def density(self, *pars):
-        return self._prop("density", *pars)
-
-    def nu_max(self, *pars):
-        return self._prop("nu_max", *pars)
-
-    def delta_nu(self, *pars):
-        return self._prop("delta_nu", *pars)
+        if not (np.all(np.isfinite([Teff, logg, feh])) and np.all(np.isfinite(mags))):
+            raise AssertionError("default star %r falls outside the model or BC grid" % (pars,))
 
     # ---- device-resident packs the fused kernels gather from ---------------------------------------------------
     @property
@@ -382,6 +350,21 @@ class ModelGridInterpolator(object):
         cols = prop_cols + ["{}_mag".format(b) for b in self.bands]
         values = np.concatenate([np.atleast_2d(props), np.atleast_2d(mags)], axis=1)
         return pd.DataFrame(values, columns=cols)
+
+
+def _column_shortcut(column):
+    def shortcut(self, *pars):
+        return self.interp_value(pars, [column]).squeeze()
+
+    shortcut.__name__ = column
+    shortcut.__doc__ = "``%s`` interpolated at ``pars`` (in ``param_names`` order); scalars or arrays." % column
+    return shortcut
+
+
+# ic.mass(*pars), ic.radius(*pars), ... — the reference's one-column conveniences (models.py:360-388)
+for _column in ("mass", "initial_mass", "radius", "Teff", "logg", "feh", "density", "nu_max", "delta_nu"):
+    setattr(ModelGridInterpolator, _column, _column_shortcut(_column))
+ModelGridInterpolator._prop = lambda self, prop, *pars: self.interp_value(pars, [prop]).squeeze()
 
 
 class EvolutionTrackInterpolator(ModelGridInterpolator):

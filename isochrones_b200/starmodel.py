@@ -94,30 +94,29 @@ class BasicStarModel(object):
         self.dec = dec
         self.obs = None
 
+        if N not in (1, 2, 3):
+            raise ValueError("N must be 1, 2 or 3")
         if N > 1 and ic.eep_replaces == "age":
             raise ValueError("Can only fit mulitple stars with IsochroneInterpolator!")
-        if N == 1:
-            if ic.eep_replaces == "age":
-                self.mass_index, self.feh_index, self.distance_index, self.AV_index = 0, 2, 3, 4
-            elif ic.eep_replaces == "mass":
-                self.age_index, self.feh_index, self.distance_index, self.AV_index = 1, 2, 3, 4
-        elif N == 2:
-            self.age_index, self.feh_index, self.distance_index, self.AV_index = 2, 3, 4, 5
-        elif N == 3:
-            self.age_index, self.feh_index, self.distance_index, self.AV_index = 3, 4, 5, 6
-        else:
-            raise ValueError("N must be 1, 2 or 3")
         self.N = N
+        # position of every shared parameter in a row: the N leading slots are the per-star parameters
+        # (mass for the single star of a track model, EEPs otherwise); see param_names
+        for slot, par in enumerate(ic.param_names):
+            if par not in ("eep",):
+                setattr(self, par + "_index", slot if slot == 0 else slot + N - 1)
 
-        kwargs.pop("use_emcee", None)
+        # observations: (value, uncertainty) pairs; NaN pairs count as "not observed" and anything that is not a
+        # pair is ignored (the reference logs a warning, starmodel.py:1423-1432)
         self.kwargs = {}
-        for k, v in kwargs.items():
+        for key, pair in kwargs.items():
+            if key == "use_emcee":
+                continue
             try:
-                val, unc = v
-                if not (np.isnan(val) or np.isnan(unc)):
-                    self.kwargs[k] = (np.float64(val), np.float64(unc))
+                value, sigma = pair
             except TypeError:
-                pass   # the reference logs "kwarg ignored" (starmodel.py:1431-1432)
+                continue
+            if not (np.isnan(value) or np.isnan(sigma)):
+                self.kwargs[key] = (np.float64(value), np.float64(sigma))
 
         self._bands = None
         self._spec_props = None
@@ -158,37 +157,25 @@ class BasicStarModel(object):
             self._ic = self._ic()
         return self._ic
 
-    @property
-    def labelstring(self):
-        return {1: "single", 2: "binary", 3: "triple"}[self.N]
+    labelstring = property(lambda self: ("single", "binary", "triple")[self.N - 1])
 
     @property
     def param_names(self):
+        """Row layout: the interpolator's names for one star; ``eep_0 .. eep_{N-1}`` then the shared ones for N > 1."""
         if self._param_names is None:
-            self._param_names = self.ic.param_names
-            if self.N == 2:
-                self._param_names = tuple(["eep_0", "eep_1"] + list(self.ic.param_names[1:]))
-            elif self.N == 3:
-                self._param_names = tuple(["eep_0", "eep_1", "eep_2"] + list(self.ic.param_names[1:]))
+            base = tuple(self.ic.param_names)
+            self._param_names = base if self.N == 1 else tuple("eep_%d" % k for k in range(self.N)) + base[1:]
         return self._param_names
 
-    @property
-    def bands(self):
-        if self._bands is None:
-            self._bands = [k for k in self.kwargs if k in self.ic.bc_grid.bands]
-        return self._bands
+    def _cached(self, attr, build):
+        if getattr(self, attr) is None:
+            setattr(self, attr, build())
+        return getattr(self, attr)
 
-    @property
-    def props(self):
-        if self._props is None:
-            self._props = [k for k in self.kwargs if k in self._not_a_band]
-        return self._props
-
-    @property
-    def spec_props(self):
-        if self._spec_props is None:
-            self._spec_props = [self.kwargs.get(k, (np.nan, np.nan)) for k in ["Teff", "logg", "feh"]]
-        return self._spec_props
+    bands = property(lambda self: self._cached("_bands", lambda: [k for k in self.kwargs if k in self.ic.bc_grid.bands]))
+    props = property(lambda self: self._cached("_props", lambda: [k for k in self.kwargs if k in self._not_a_band]))
+    spec_props = property(lambda self: self._cached(
+        "_spec_props", lambda: [self.kwargs.get(k, (np.nan, np.nan)) for k in ("Teff", "logg", "feh")]))
 
     @property
     def n_params(self):
@@ -363,22 +350,17 @@ class BasicStarModel(object):
         return df[names].values if values else df
 
 
-class SingleStarModel(BasicStarModel):
+def _fixed_multiplicity(name, n_stars):
+    """``BasicStarModel`` with the number of stars pinned (the reference's Single / Binary / TripleStarModel)."""
     def __init__(self, *args, **kwargs):
-        kwargs["N"] = 1
-        super().__init__(*args, **kwargs)
+        BasicStarModel.__init__(self, *args, **dict(kwargs, N=n_stars))
+
+    return type(name, (BasicStarModel,), {"__init__": __init__, "__doc__": "%d-star ``BasicStarModel``." % n_stars})
 
 
-class BinaryStarModel(BasicStarModel):
-    def __init__(self, *args, **kwargs):
-        kwargs["N"] = 2
-        super().__init__(*args, **kwargs)
-
-
-class TripleStarModel(BasicStarModel):
-    def __init__(self, *args, **kwargs):
-        kwargs["N"] = 3
-        super().__init__(*args, **kwargs)
+SingleStarModel = _fixed_multiplicity("SingleStarModel", 1)
+BinaryStarModel = _fixed_multiplicity("BinaryStarModel", 2)
+TripleStarModel = _fixed_multiplicity("TripleStarModel", 3)
 
 
 def compile_catalog(models):
