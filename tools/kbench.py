@@ -36,6 +36,11 @@ def main():
         # bound experiments: every row identical (all gathers broadcast: the L1 data pipe costs nothing) and rows
         # sharing one cell (distinct weights, same 24 nodes)
         "identical": lambda s: np.tile(truth, (n, 1)),
+        # groups of 2 / 4 / 8 consecutive rows identical: every gather instruction touches 16 / 8 / 4 distinct lines
+        # instead of 32 — the L1 wavefront count lane-cooperative loads would have, without their overhead
+        "pair_same": lambda s: np.repeat(syn.posterior_like_batch("track", n // 2, truth, n_eep=n_eep, seed=2 + s), 2, axis=0),
+        "quad_same": lambda s: np.repeat(syn.posterior_like_batch("track", n // 4, truth, n_eep=n_eep, seed=2 + s), 4, axis=0),
+        "oct_same": lambda s: np.repeat(syn.posterior_like_batch("track", n // 8, truth, n_eep=n_eep, seed=2 + s), 8, axis=0),
         "one_cell": lambda s: truth + np.array([0.004, 0.4, 0.01, 2.0, 0.02]) * np.random.RandomState(s).random_sample((n, 5)),
     }
     d_out = ctx.dev_alloc(n * 8)
