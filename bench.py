@@ -389,6 +389,104 @@ def extra_workloads(ctx, bc, args, peak):
     return out
 
 
+def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks):
+    """BASELINE.json configs 4 and 5 on N GPUs (every rank runs this; rank 0 reports):
+    configs[4]: BinaryStarModel lnpost batch of 1e6 rows IN TOTAL, rows sharded in contiguous blocks (RowSharder), the
+    per-row results all-gathered so that every rank holds the full lnpost vector (what a sampler's acceptance step
+    needs); configs[3]: a catalog of 10 000 independent star models, the STARS sharded across ranks (each rank stages
+    only its own models), 100 rows per star per step, results all-gathered."""
+    import pandas as pd
+
+    import isochrones_b200 as ib
+    from isochrones_b200 import parallel, synthetic as syn
+    from isochrones_b200.catalog import StarCatalog
+
+    out = {}
+    iso = syn.make_iso_grid(columns=("Teff", "logg", "feh", "Mbol", "mass", "dm_deep", "nu_max", "delta_nu"))
+    ic = ib.ichrone_from_arrays("iso", iso, bc, ctx=ctx)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            fn()
+        ms = max_over_ranks(ctx.timer_stop()) / args.steps
+        barrier()
+        return ms
+
+    # ---- configs[4]: binary star, 1e6 rows in total ---------------------------------------------------------------
+    truth = syn.default_truth("iso", n_stars=2)
+    _, _, _, mags = ic.interp_mag([truth[0]] + list(truth[2:]), list(BANDS))
+    obs = {b: (float(np.round(m, 3)) - 0.35, 0.02) for b, m in zip(BANDS, mags)}
+    binary = ib.BinaryStarModel(ic, Teff=(5772.0, 80.0), logg=(4.44, 0.1), feh=(0.0, 0.1), parallax=(10.0, 0.1), **obs)
+    rows = syn.posterior_like_batch("iso", BATCH, truth, seed=70)       # same seed on every rank: one global batch
+    rows[:, :2] = -np.sort(-rows[:, :2], axis=1)
+    sh = parallel.RowSharder(BATCH, world, rank)
+    mine = np.ascontiguousarray(sh.local(rows))
+    d_p = ctx.dev_alloc(max(mine.nbytes, 8))
+    ctx.h2d(d_p, mine)
+    d_o, d_all = ctx.dev_alloc(sh.pad * 8), ctx.dev_alloc(world * sh.pad * 8)
+    n_mine = len(mine)
+    ms_k = timed(lambda: binary.compiled.lnpost_device(d_p, n_mine, d_o))
+    ms_g = timed(lambda: (binary.compiled.lnpost_device(d_p, n_mine, d_o), comm.allgather(d_o, sh.pad, d_all)))
+    got = np.empty((world, sh.pad))
+    ctx.d2h(got, d_all)
+    full = sh.assemble(got)
+    out["binary_1e6_rows_sharded"] = {
+        "value": BATCH / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "ms_per_step_without_gather": ms_k,
+        "rows_per_gpu": sh.pad, "finite_frac": float(np.isfinite(full).mean()), "scaling": "strong",
+        "config": "configs[4]: BinaryStarModel, iso grid 107x15x1710, 4 bands + parallax, 1e6 rows in total sharded over "
+                  "%d GPUs, ncclAllGather of lnpost (%d B per rank) inside the timed step" % (world, sh.pad * 8)}
+    for d in (d_p, d_o, d_all):
+        ctx.dev_free(d)
+
+    # ---- configs[3]: catalog, stars sharded ---------------------------------------------------------------------
+    n_stars, rows_per_star = 10_000, 100
+    truth1 = syn.default_truth("iso", n_stars=1)
+    rng = np.random.RandomState(8)
+    t = np.tile(truth1, (n_stars, 1))
+    t[:, 0] = rng.uniform(300.0, 900.0, n_stars)
+    t[:, 1] = rng.uniform(9.0, 9.9, n_stars)
+    t[:, 2] = rng.uniform(-0.5, 0.3, n_stars)
+    t[:, 3] = rng.uniform(50.0, 400.0, n_stars)
+    t[:, 4] = rng.uniform(0.0, 0.5, n_stars)
+    ssh = parallel.RowSharder(n_stars, world, rank)
+    a, b = ssh.bounds()
+    tm = t[a:b]
+    _, _, _, mg = ic.interp_mag([tm[:, j] for j in range(5)], list(BANDS))
+    table = {"parallax": 1000.0 / tm[:, 3], "parallax_unc": np.full(b - a, 0.1)}
+    for j, bn in enumerate(BANDS):
+        table[bn + "_mag"] = mg[:, j]
+        table[bn + "_mag_unc"] = np.full(b - a, 0.02)
+    compiled = StarCatalog(pd.DataFrame(table), props=["parallax"]).compile(ic)
+    mor = np.repeat(np.arange(b - a, dtype=np.int32), rows_per_star)
+    pars = np.repeat(tm, rows_per_star, axis=0)
+    pars *= 1 + 0.002 * np.random.RandomState(80 + rank).standard_normal(pars.shape)
+    n_rows, pad = len(pars), ssh.pad * rows_per_star
+    d_p, d_m = ctx.dev_alloc(pars.nbytes), ctx.dev_alloc(mor.nbytes)
+    d_o, d_all = ctx.dev_alloc(pad * 8), ctx.dev_alloc(world * pad * 8)
+    ctx.h2d(d_p, pars)
+    ctx.h2d(d_m, mor)
+    ms_k = timed(lambda: compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m))
+    ms_g = timed(lambda: (compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m), comm.allgather(d_o, pad, d_all)))
+    got = np.empty((world, pad))
+    ctx.d2h(got, d_all)
+    total_rows = n_stars * rows_per_star
+    out["catalog_10k_stars_sharded"] = {
+        "value": total_rows / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "ms_per_step_without_gather": ms_k,
+        "stars_per_gpu": ssh.pad, "rows_per_gpu": pad,
+        "finite_frac": float(np.isfinite(np.concatenate([got[r, :ssh.counts[r] * rows_per_star] for r in range(world)])).mean()),
+        "scaling": "strong",
+        "config": "configs[3] shape: 10 000 star models sharded over %d GPUs (each rank stages only its own stars), "
+                  "100 rows per star per step (1e6 rows in total), ncclAllGather of lnpost inside the timed step" % world}
+    for d in (d_p, d_m, d_o, d_all):
+        ctx.dev_free(d)
+    return out
+
+
 def timed_device_loop(ctx, compiled, d_batches, d_out, steps, warmup, barrier=None):
     for s in range(warmup):
         compiled.lnpost_device(d_batches[s % len(d_batches)], BATCH, d_out)
@@ -520,6 +618,8 @@ def main():
         barrier()
         allgather = {"ms_per_step_with_gather": ms_g / args.steps, "value_with_gather": world * BATCH * args.steps / (ms_g * 1e-3),
                      "bytes_per_rank_per_step": BATCH * 8, "collective": "ncclAllGather f64 on the compute stream"}
+        ctx.dev_free(d_all)
+        sharded = None if args.no_extras else sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
 
     if rank != 0:
         if dist is not None:
@@ -554,6 +654,8 @@ def main():
 
     if world == 1 and not args.no_extras:
         alt.update(extra_workloads(ctx, bc, args, peak))
+    if world > 1 and sharded:
+        alt.update(sharded)
 
     achieved = B_ALG * BATCH / (kernel_ms * 1e-3) / 1e9
     traffic = None
