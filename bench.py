@@ -275,6 +275,43 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def interp_workloads(ctx, ic, truth, n_eep, args):
+    """BASELINE.json configs[0] at bench size: the standalone interpolation entry points (DFInterpolator /
+    interp_value, interp_mag) on 1e6 points through the host-pointer C ABI (pinned buffers; H2D + kernel + D2H)."""
+    from isochrones_b200 import synthetic as syn
+
+    out = {}
+    pts = syn.posterior_like_batch("track", BATCH, truth, n_eep=n_eep, seed=321)
+    xs = [ctx.pinned_empty((BATCH,)) for _ in range(5)]
+    for j in range(5):
+        xs[j][:] = pts[:, j]
+    props = ["Teff", "logg", "nu_max"]
+    vout = ctx.pinned_empty((BATCH, len(props)))
+    for _ in range(3):
+        ic.interp_value(xs[:3], props, out=vout)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v = ic.interp_value(xs[:3], props, out=vout)
+    dt = (time.perf_counter() - t0) / args.steps
+    out["interp_value_3_props"] = {
+        "value": BATCH / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "finite_frac": float(np.isfinite(v).mean()),
+        "config": "configs[0] shape at 1e6 points: ModelGridInterpolator.interp_value((mass, eep, feh), 3 props, out=pinned) "
+                  "-> iso_interp_values, host arrays in / out (48 B per point over PCIe)"}
+    outs = (ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)),
+            ctx.pinned_empty((BATCH, len(BANDS))))
+    for _ in range(3):
+        ic.interp_mag(xs, list(BANDS), out=outs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ic.interp_mag(xs, list(BANDS), out=outs)
+    dt = (time.perf_counter() - t0) / args.steps
+    out["interp_mag_4_bands"] = {
+        "value": BATCH / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "finite_frac": float(np.isfinite(r[3]).mean()),
+        "config": "ModelGridInterpolator.interp_mag(5 parameter arrays, VJHK, out=pinned arrays) -> iso_interp_mags, "
+                  "host arrays in / out (96 B per point over PCIe + one host-side pack of the [5, N] block)"}
+    return out
+
+
 def extra_workloads(ctx, bc, args, peak):
     """BASELINE.json configs 3 and 5 on one GPU (informational "alt" entries; parity for them lives in tests/):
     binary-star lnpost batch on the isochrone grid, and the on-device ensemble sampler (256 walkers x 2000 steps as
@@ -653,11 +690,20 @@ def main():
             ctx.dev_free(d)
 
     if world == 1 and not args.no_extras:
+        alt.update(interp_workloads(ctx, ic, truth, n_eep, args))
         alt.update(extra_workloads(ctx, bc, args, peak))
     if world > 1 and sharded:
         alt.update(sharded)
 
     achieved = B_ALG * BATCH / (kernel_ms * 1e-3) / 1e9
+    # The unit that actually limits the kernel: every corner record is a scattered 32-byte sector, and
+    # the L1 data pipe of an SM retires one such sector ("wavefront") per clock, whatever level of the hierarchy
+    # holds it.  32 sectors per row: 8 corners x 2 (model pack) + 16 corners x 1 (BC pack, one chunk of 4 bands).
+    sectors_per_row = 8 * 2 + 16 * 1
+    info = ctx.info()
+    sm_hz = float(clock_summary.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    l1_peak = info["sm_count"] * sm_hz
+    l1_ach = sectors_per_row * BATCH / (kernel_ms * 1e-3)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -685,7 +731,14 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "iso_lnpost_kernel<1,false>", "algorithmic_bytes_per_eval": B_ALG,
-                     "peak_source": peak_src, "kernel_ms": kernel_ms},
+                     "peak_source": peak_src, "kernel_ms": kernel_ms,
+                     "l1_gather_bound": {"sectors_per_eval": sectors_per_row, "achieved_sectors_per_s": l1_ach,
+                                         "peak_sectors_per_s": l1_peak, "frac": l1_ach / l1_peak,
+                                         "note": "scattered 32-byte sector gathers at 1 sector per clock per SM "
+                                                 "(%d SMs x %.0f MHz): the bound of a thread-per-row gather kernel; "
+                                                 "lanes that share a 128-byte line are counted once by the hardware, "
+                                                 "so the counter-based figure (ncu l1tex__data_pipe_lsu_wavefronts) is "
+                                                 "lower" % (info["sm_count"], sm_hz / 1e6)}},
         "alt": alt,
     }
     if allgather:

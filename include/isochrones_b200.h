@@ -101,6 +101,12 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
                     int i_Teff, int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands,
                     const double *h_pars, int64_t N, double *h_Teff, double *h_logg, double *h_feh,
                     double *h_mags);
+/* The same with the five parameters as separate [N] arrays (what ModelGridInterpolator.interp_mag holds before the
+ * reference stacks them into pars[5, N] at models.py:416-424): saves the caller that host-side copy. */
+int iso_interp_mags_cols(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5],
+                         int i_Teff, int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands,
+                         const double *const *h_par, int64_t N, double *h_Teff, double *h_logg, double *h_feh,
+                         double *h_mags);
 
 /* interp_eeps (interp.py:488-499) over interp_eep (:502-558): (age, feh, mass) -> EEP on an evolution-track grid
  * staged as a 3-D (feh, mass, eep) iso_grid whose column i_age holds log10 age (the per-track age arrays of

@@ -90,6 +90,8 @@ SIGNATURES = {
     "iso_interp_values": (C.c_int, [_VP, _VP, C.POINTER(c_double_p), C.c_int64, c_int32_p, C.c_int, c_double_p]),
     "iso_interp_mags": (C.c_int, [_VP, _VP, _VP, c_int32_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, C.c_int,
                                   c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "iso_interp_mags_cols": (C.c_int, [_VP, _VP, _VP, c_int32_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, C.c_int,
+                                       C.POINTER(c_double_p), C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
     "iso_interp_eeps": (C.c_int, [_VP, _VP, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "iso_prior_eval": (C.c_int, [_VP, C.POINTER(IsoPrior), C.c_int, c_double_p, C.c_int64, c_double_p]),
     "iso_models_stage": (C.c_int, [_VP, C.POINTER(IsoModel), C.c_int, C.POINTER(_VP)]),
@@ -274,11 +276,14 @@ class DeviceGrid:
         self.ctx.check(lib().iso_grid_repack(self.ctx.handle, self.handle, ip(cols), len(cols), ncols_out, C.byref(h)))
         return DeviceGrid(self.ctx, handle=h)
 
-    def interp_values(self, xx, icols):
+    def interp_values(self, xx, icols, out=None):
         xx = [f64(a) for a in xx]
         n = len(xx[0])
         icols = np.ascontiguousarray(icols, dtype=np.int32)
-        out = np.empty((n, len(icols)), dtype=np.float64)
+        if out is None:
+            out = np.empty((n, len(icols)), dtype=np.float64)
+        elif out.shape != (n, len(icols)) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float64 array of shape [N, ncols]")
         ptrs = (c_double_p * self.ndim)(*[dp(a) for a in xx])
         self.ctx.check(lib().iso_interp_values(self.ctx.handle, self.handle, ptrs, n, ip(icols), len(icols), dp(out)))
         return out

@@ -295,9 +295,10 @@ int iso_interp_values(iso_ctx *ctx, const iso_grid *grid, const double *const *h
     return iso_run_pipeline(ctx, N, arr, ndim + 1, interp_launch, &u);
 }
 
-int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5], int i_Teff,
-                    int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands, const double *h_pars,
-                    int64_t N, double *h_Teff, double *h_logg, double *h_feh, double *h_mags)
+int iso_interp_mags_cols(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5], int i_Teff,
+                         int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands,
+                         const double *const *h_par /* 5 pointers, each [N] */, int64_t N, double *h_Teff, double *h_logg,
+                         double *h_feh, double *h_mags)
 {
     if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_mags: ctx is NULL");
     ISO_REQUIRE(ctx, model && bc && index_order, "iso_interp_mags: NULL argument");
@@ -313,13 +314,14 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
     for (int j = 0; j < 5; j++)
         ISO_REQUIRE(ctx, index_order[j] >= 0 && index_order[j] < 5, "iso_interp_mags: bad index_order");
     if (N == 0) return ISO_OK;
-    ISO_REQUIRE(ctx, h_pars && h_Teff && h_logg && h_feh && (n_bands == 0 || h_mags), "iso_interp_mags: NULL buffer");
+    ISO_REQUIRE(ctx, h_par && h_Teff && h_logg && h_feh && (n_bands == 0 || h_mags), "iso_interp_mags: NULL buffer");
+    for (int j = 0; j < 5; j++) ISO_REQUIRE(ctx, h_par[j], "iso_interp_mags: NULL parameter array");
     IsoDeviceGuard guard(ctx->device);
     DevInts cols;
     int rc = cols.upload(ctx, bc_cols, n_bands);
     if (rc != ISO_OK) return rc;
     IsoPipeArray arr[9];
-    for (int j = 0; j < 5; j++) arr[j] = IsoPipeArray{h_pars + (size_t)j * N, nullptr, 8};
+    for (int j = 0; j < 5; j++) arr[j] = IsoPipeArray{h_par[j], nullptr, 8};
     arr[5] = IsoPipeArray{nullptr, h_Teff, 8};
     arr[6] = IsoPipeArray{nullptr, h_logg, 8};
     arr[7] = IsoPipeArray{nullptr, h_feh, 8};
@@ -335,6 +337,18 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
     u.proto.bc_cols = cols.d;
     u.proto.n_bands = n_bands;
     return iso_run_pipeline(ctx, N, arr, 9, mags_launch, &u);
+}
+
+int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5], int i_Teff,
+                    int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands, const double *h_pars,
+                    int64_t N, double *h_Teff, double *h_logg, double *h_feh, double *h_mags)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_mags: ctx is NULL");
+    ISO_REQUIRE(ctx, N <= 0 || h_pars, "iso_interp_mags: NULL buffer");
+    const double *par[5];
+    for (int j = 0; j < 5; j++) par[j] = h_pars ? h_pars + (size_t)j * (size_t)(N > 0 ? N : 0) : nullptr;
+    return iso_interp_mags_cols(ctx, model, bc, index_order, i_Teff, i_logg, i_feh, i_Mbol, bc_cols, n_bands, par, N, h_Teff,
+                                h_logg, h_feh, h_mags);
 }
 
 int iso_interp_eeps(iso_ctx *ctx, const iso_grid *track_grid, int i_age, const int32_t *h_lengths, const double *h_age,

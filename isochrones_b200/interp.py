@@ -103,7 +103,9 @@ class DFInterpolator(object):
         self.n_columns = len(self.columns)
         self._device_grid = None
 
-    def __call__(self, p, cols="all"):
+    def __call__(self, p, cols="all", out=None):
+        """``interp(p, cols)`` of the reference (interp.py:631-672).  ``out`` (optional, array calls): a C-contiguous
+        float64 ``[N, len(cols)]`` array to fill (a page-locked one is written by DMA directly)."""
         if isinstance(cols, str) and cols == "all":
             icols = np.arange(self.n_columns)
         else:
@@ -115,6 +117,8 @@ class DFInterpolator(object):
             pp = [np.array([x], dtype=float) for x in p]
         else:
             b = np.broadcast(*p)
-            pp = [np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel() for x in p]
-        values = self.device_grid.interp_values(pp, icols)
+            # coordinates that already are full-size float64 arrays are passed as they are (no np.resize copy)
+            pp = [np.ravel(x) if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.size == b.size
+                  else np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel() for x in p]
+        values = self.device_grid.interp_values(pp, icols, out=None if scalar else out)
         return values[0] if scalar else values

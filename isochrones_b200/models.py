@@ -185,9 +185,10 @@ class ModelGridInterpolator(object):
         return self._bc_packs[key]
 
     # ---- the hot entry points -----------------------------------------------------------------------------
-    def interp_value(self, pars, props):
+    def interp_value(self, pars, props, out=None):
         """pars : (mass, eep, feh[, distance, AV]) for tracks / (eep, age, feh[, ..]) for isochrones
-        (models.py:390-400); scalars give ``[len(props)]``, arrays ``[N, len(props)]``."""
+        (models.py:390-400); scalars give ``[len(props)]``, arrays ``[N, len(props)]`` (``out``: optional array to
+        fill, see ``DFInterpolator.__call__``)."""
         i0, i1, i2 = self.param_index_order[:3]
         try:
             pars = np.atleast_1d(pars[self.param_index_order])
@@ -198,33 +199,55 @@ class ModelGridInterpolator(object):
             p = [pars[i0], pars[i1], pars[i2]]
         if isinstance(props, str):
             props = [props]
-        return self.model_grid.interp(p, props)
+        return self.model_grid.interp(p, props, out=out)
 
-    def interp_mag(self, pars, bands):
+    def interp_mag(self, pars, bands, out=None):
         """pars : five parameters in ``param_names`` order; returns ``(Teff, logg, feh, mags)`` — scalars and a
-        ``[n_bands]`` array for a single point, ``[N]`` arrays and ``[N, n_bands]`` otherwise (models.py:402-445)."""
+        ``[n_bands]`` array for a single point, ``[N]`` arrays and ``[N, n_bands]`` otherwise (models.py:402-445).
+
+        ``out`` (optional, batch calls): ``(Teff[N], logg[N], feh[N], mags[N, n_bands])`` float64 arrays to fill —
+        page-locked ones (``ctx.pinned_empty``) are written by DMA directly.  The reference stacks the broadcast
+        parameters into ``pars[5, N]`` (``np.resize`` per parameter, models.py:416-424); here parameters that already
+        are full-size float64 arrays go to the device as they are (``iso_interp_mags_cols``)."""
         bands = list(bands) if bands is not None else []
         scalar = False
         try:
-            p = np.atleast_1d(pars).astype(float).squeeze()
-            if p.ndim > 1 or p.shape != (5,):
+            # a single point: five scalars (checked before any array conversion — the parameters may be large arrays)
+            if not (isinstance(pars, np.ndarray) or all(np.ndim(x) == 0 or np.size(x) == 1 for x in pars)):
+                raise ValueError
+            q = np.atleast_1d(pars).astype(float).squeeze()
+            if q.ndim > 1 or q.shape != (5,):
                 raise ValueError
             scalar = True
-            p = p.reshape(5, 1)
+            n = 1
+            cols = [q[j:j + 1].copy() for j in range(5)]
         except (TypeError, ValueError):
             b = np.broadcast(*pars)
-            p = np.array([np.resize(x, b.shape).astype(float).ravel() for x in pars])
-        p = np.ascontiguousarray(p, dtype=np.float64)
-        n = p.shape[1]
+            n = int(b.size)
+            cols = []
+            for x in pars:
+                if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.size == n and x.flags["C_CONTIGUOUS"]:
+                    cols.append(x.reshape(-1))
+                elif np.ndim(x) == 0:
+                    cols.append(np.full(n, float(x)))
+                else:   # the reference's np.resize semantics (cyclic repeat of the flattened values, models.py:419)
+                    cols.append(np.ascontiguousarray(np.resize(x, b.shape), dtype=np.float64).ravel())
         bc, = (self.bc_pack(bands),)
-        teff, logg, feh = np.empty(n), np.empty(n), np.empty(n)
-        mags = np.empty((n, len(bands)))
+        if out is not None and not scalar:
+            teff, logg, feh, mags = out
+            for a, shp in ((teff, (n,)), (logg, (n,)), (feh, (n,)), (mags, (n, len(bands)))):
+                if a.shape != shp or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out arrays must be C-contiguous float64 of shapes [N], [N], [N], [N, n_bands]")
+        else:
+            teff, logg, feh = np.empty(n), np.empty(n), np.empty(n)
+            mags = np.empty((n, len(bands)))
         io = np.array(self.param_index_order, dtype=np.int32)
         bc_cols = np.arange(len(bands), dtype=np.int32)
+        ptrs = (_lib.c_double_p * 5)(*[_lib.dp(c) for c in cols])
         ctx = self.ctx
-        ctx.check(_lib.lib().iso_interp_mags(
+        ctx.check(_lib.lib().iso_interp_mags_cols(
             ctx.handle, self.model_pack.handle, bc.handle, _lib.ip(io), 0, 1, 2, 3, _lib.ip(bc_cols), len(bands),
-            _lib.dp(p), n, _lib.dp(teff), _lib.dp(logg), _lib.dp(feh), _lib.dp(mags)))
+            ptrs, n, _lib.dp(teff), _lib.dp(logg), _lib.dp(feh), _lib.dp(mags)))
         if scalar:
             return float(teff[0]), float(logg[0]), float(feh[0]), mags[0]
         return teff, logg, feh, mags

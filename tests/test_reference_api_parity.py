@@ -45,7 +45,8 @@ def test_interpolator_and_models():
     from isochrones_b200 import interp as I, models as M
 
     assert _params(I.DFInterpolator.__init__)[:4] == _params(ref.interp.DFInterpolator.__init__)
-    assert _params(I.DFInterpolator.__call__) == _params(ref.interp.DFInterpolator.__call__)
+    # the reference's parameters first, in order; the product only appends optional keywords (out=)
+    assert _params(I.DFInterpolator.__call__)[:2] == _params(ref.interp.DFInterpolator.__call__)
     for meth in ("add_column", "_make_grid"):
         assert _params(getattr(I.DFInterpolator, meth)) == _params(getattr(ref.interp.DFInterpolator, meth))
     for name in ("EvolutionTrackInterpolator", "IsochroneInterpolator"):
