@@ -275,9 +275,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def interp_workloads(ctx, ic, truth, n_eep, args):
+def interp_workloads(ctx, ic, truth, n_eep, args, mod=None):
     """BASELINE.json configs[0] at bench size: the standalone interpolation entry points (DFInterpolator /
-    interp_value, interp_mag) on 1e6 points through the host-pointer C ABI (pinned buffers; H2D + kernel + D2H)."""
+    interp_value, interp_mag) on 1e6 points through the host-pointer C ABI (pinned buffers; H2D + kernel + D2H), and
+    the latency of the reference-shaped small calls (scalar lnpost, one 128-row half-step)."""
     from isochrones_b200 import synthetic as syn
 
     out = {}
@@ -297,6 +298,32 @@ def interp_workloads(ctx, ic, truth, n_eep, args):
         "value": BATCH / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "finite_frac": float(np.isfinite(v).mean()),
         "config": "configs[0] shape at 1e6 points: ModelGridInterpolator.interp_value((mass, eep, feh), 3 props, out=pinned) "
                   "-> iso_interp_values, host arrays in / out (48 B per point over PCIe)"}
+    # the reference's scalar interface, as emcee / MultiNest call it: one lnpost(p) per Python call, and a
+    # 128-row batch (one emcee half-step of 256 walkers) through lnpost_batch on pageable arrays
+    if mod is not None:
+        p1 = list(pts[0])
+        for _ in range(200):
+            mod.lnpost(p1)
+        reps = 2000
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            mod.lnpost(p1)
+        dt = (time.perf_counter() - t0) / reps
+        out["scalar_lnpost_call"] = {
+            "value": 1.0 / dt, "unit": UNIT, "us_per_call": dt * 1e6,
+            "config": "BasicStarModel.lnpost(p): one row per call through the C ABI (H2D, one-row launch, D2H, sync); "
+                      "the reference's own scalar call takes 68-93 us in the build container, 369 us published"}
+        half = np.ascontiguousarray(pts[:128])
+        for _ in range(200):
+            mod.lnpost_batch(half)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            mod.lnpost_batch(half)
+        dt = (time.perf_counter() - t0) / reps
+        out["emcee_half_step_128_rows_from_host"] = {
+            "value": 128.0 / dt, "unit": UNIT, "us_per_call": dt * 1e6,
+            "config": "BasicStarModel.lnpost_batch on a pageable [128, 5] array: what a host-driven emcee (vectorize=True) "
+                      "pays per half-step of a 256-walker ensemble"}
     outs = (ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)),
             ctx.pinned_empty((BATCH, len(BANDS))))
     for _ in range(3):
@@ -690,7 +717,7 @@ def main():
             ctx.dev_free(d)
 
     if world == 1 and not args.no_extras:
-        alt.update(interp_workloads(ctx, ic, truth, n_eep, args))
+        alt.update(interp_workloads(ctx, ic, truth, n_eep, args, mod=mod))
         alt.update(extra_workloads(ctx, bc, args, peak))
     if world > 1 and sharded:
         alt.update(sharded)

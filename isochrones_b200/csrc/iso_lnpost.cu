@@ -294,7 +294,8 @@ static int mnest_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t r
     int blocks = (int)((total + 255) / 256 < ctx->prop.multiProcessorCount * 8 ? (total + 255) / 256
                                                                                 : ctx->prop.multiProcessorCount * 8);
     // in place: the output array aliases the input rows (d[1] receives a device-side copy below)
-    ISO_CUDA(ctx, cudaMemcpyAsync(d[1], d[0], (size_t)total * 8, cudaMemcpyDeviceToDevice, st));
+    // (the buffers are device memory, or page-locked host memory on the small-call path: cudaMemcpyDefault)
+    if (d[1] != d[0]) ISO_CUDA(ctx, cudaMemcpyAsync(d[1], d[0], (size_t)total * 8, cudaMemcpyDefault, st));
     iso_mnest_prior_kernel<<<blocks, 256, 0, st>>>((double *)d[1], u->d_lo, u->d_hi, u->ndim, total);
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());

@@ -14,6 +14,13 @@
 #define ISO_PIPE_PAGEABLE_DEFAULT 0
 #endif
 #define ISO_PIPE_REGISTER_MIN_BYTES (4 << 20)
+// Calls of at most this many rows (the reference's scalar lnpost(p), one emcee half-step, ..) skip the copy engine:
+// the kernel reads its rows from, and writes its results to, page-locked HOST memory directly (pinned memory is
+// device-addressable under unified addressing), so the call is one launch + one stream synchronisation instead of
+// H2D copy + launch + D2H copy + synchronisation.
+#ifndef ISO_PIPE_ZERO_COPY_ROWS
+#define ISO_PIPE_ZERO_COPY_ROWS 512
+#endif
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
@@ -79,6 +86,43 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         const char *e = getenv("ISO_PIPE_PAGEABLE");
         return e ? atoi(e) : ISO_PIPE_PAGEABLE_DEFAULT;
     }();
+    static const int64_t zero_copy_rows = [] {
+        const char *e = getenv("ISO_PIPE_ZERO_COPY_ROWS");
+        return (int64_t)(e ? atoll(e) : ISO_PIPE_ZERO_COPY_ROWS);
+    }();
+    if (n_rows <= zero_copy_rows) {
+        // small-call path: caller buffers that are page-locked are handed to the kernel as they are, pageable ones go
+        // through the context's pinned staging buffer (one host memcpy each way); ordered on the compute stream
+        int64_t soff[ISO_PIPE_MAX_ARRAYS + 1];
+        bool direct[ISO_PIPE_MAX_ARRAYS];
+        soff[0] = 0;
+        for (int k = 0; k < n_arrays; k++) {
+            const void *h = arrays[k].h_in ? arrays[k].h_in : arrays[k].h_out;
+            direct[k] = h != nullptr && is_pinned(h);
+            soff[k + 1] = soff[k] + ((h != nullptr && !direct[k]) ? align256(n_rows * arrays[k].row_bytes) : 0);
+        }
+        int rc = iso_stage_reserve(ctx, 0, 0, soff[n_arrays]);
+        if (rc != ISO_OK) return rc;
+        void *d_arrays[ISO_PIPE_MAX_ARRAYS];
+        for (int k = 0; k < n_arrays; k++) {
+            const void *h = arrays[k].h_in ? arrays[k].h_in : arrays[k].h_out;
+            d_arrays[k] = nullptr;
+            if (!h) continue;
+            if (direct[k]) {
+                d_arrays[k] = const_cast<void *>(h);
+            } else {
+                d_arrays[k] = (char *)ctx->h_stage[0] + soff[k];
+                if (arrays[k].h_in) memcpy(d_arrays[k], arrays[k].h_in, (size_t)(n_rows * arrays[k].row_bytes));
+            }
+        }
+        rc = launch(ctx, ctx->stream, d_arrays, 0, n_rows, user);
+        if (rc != ISO_OK) return rc;
+        ISO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < n_arrays; k++)
+            if (d_arrays[k] && arrays[k].h_out && !direct[k])
+                memcpy(arrays[k].h_out, d_arrays[k], (size_t)(n_rows * arrays[k].row_bytes));
+        return ISO_OK;
+    }
     int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
     int64_t off[ISO_PIPE_MAX_ARRAYS + 1];
     bool pinned[ISO_PIPE_MAX_ARRAYS];
