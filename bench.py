@@ -725,8 +725,9 @@ def main():
     achieved = B_ALG * BATCH / (kernel_ms * 1e-3) / 1e9
     # The unit that actually limits the kernel: every corner record is a scattered 32-byte sector, and
     # the L1 data pipe of an SM retires one such sector ("wavefront") per clock, whatever level of the hierarchy
-    # holds it.  32 sectors per row: 8 corners x 2 (model pack) + 16 corners x 1 (BC pack, one chunk of 4 bands).
-    sectors_per_row = 8 * 2 + 16 * 1
+    # holds it.  28 sectors per row: 4 EEP-pair records x 3 (model pack, 96-byte records of 2 x 6 columns) + 16 corners
+    # x 1 (BC pack, one chunk of 4 bands) = 896 B, i.e. exactly the algorithmic 8 x 6 x 8 + 16 x 4 x 8 bytes.
+    sectors_per_row = 4 * 3 + 16 * 1
     info = ctx.info()
     sm_hz = float(clock_summary.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
     l1_peak = info["sm_count"] * sm_hz

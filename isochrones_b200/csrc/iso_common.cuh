@@ -17,6 +17,11 @@
 
 #define ISO_LOG_ONE_OVER_ROOT_2PI (-0.91893853320467274178)
 #define ISO_PAD_NODES 2   // all-zero nodes appended to every staged grid
+// EEP-pair records of a model pack (what the fused row kernels gather): record r holds the six columns every row
+// needs (Teff, logg, feh, Mbol, age|mass, dt_deep|dm_deep) of flat node r AND of flat node r + 1 — the two
+// EEP-adjacent corners of a cell — in 96 bytes = 3 sectors, instead of 2 x 64-byte nodes = 4 sectors.
+#define ISO_PP_NCOLS 6
+#define ISO_PP_STRIDE 12
 
 // ------------------------------------------------------------------------------------------------
 // host-side objects behind the opaque handles
@@ -32,6 +37,7 @@ struct IsoAxisDev {
 
 struct IsoGridDev {     // by-value kernel argument
     const double *g;    // [n_nodes + ISO_PAD_NODES][ncols]
+    const double *gp;   // model packs only: EEP-pair records [n_nodes + ISO_PAD_NODES][ISO_PP_STRIDE] (or NULL)
     const double2 *nodes;   // concatenated axis tables
     long long n_nodes;
     int ndim, ncols;
@@ -45,6 +51,7 @@ struct iso_grid {
     IsoGridDev dev;
     double *d_grid = nullptr;
     double2 *d_nodes = nullptr;
+    double *d_pair = nullptr;               // EEP-pair records, built on first use by a row kernel (iso_grid_pair_pack)
     std::vector<double> h_axes[ISO_MAX_DIM];
     int64_t shape[ISO_MAX_DIM + 1];
     int device = 0;
@@ -73,6 +80,7 @@ struct iso_ctx {
 int iso_set_error(iso_ctx *ctx, int code, const char *fmt, ...);
 int iso_check_cuda(iso_ctx *ctx, cudaError_t e, const char *what);
 int iso_stage_reserve(iso_ctx *ctx, int slot, int64_t dev_bytes, int64_t host_bytes);
+int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack);   // builds model_pack->d_pair if absent
 
 // Chunked, double-buffered host<->device pipeline of the host-pointer entry points: alternating chunks run
 // H2D -> kernel -> D2H on the two copy streams so the transfers of one chunk overlap the kernel of the other.

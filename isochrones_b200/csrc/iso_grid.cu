@@ -26,6 +26,42 @@ __global__ void iso_repack_kernel(const double *__restrict__ src, int src_ncols,
     }
 }
 
+// EEP-pair records of an 8-column model pack (ISO_PP_*): record r = columns 0..5 of node r, then of node r + 1.
+// Node r + 1 follows the reference's flat (unchecked) index arithmetic: past the last node it is the all-zero
+// padding node, and the padding records themselves are all-zero.
+__global__ void iso_pair_pack_kernel(const double *__restrict__ src, long long n_nodes, double *__restrict__ dst)
+{
+    const long long total = (n_nodes + ISO_PAD_NODES) * (long long)ISO_PP_STRIDE;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long rec = t / ISO_PP_STRIDE;
+        const int r = (int)(t - rec * ISO_PP_STRIDE);
+        const int half = r / ISO_PP_NCOLS, c = r - half * ISO_PP_NCOLS;
+        dst[t] = rec < n_nodes ? src[(rec + half) * ISO_MP_NCOLS + c] : 0.0;   // rec + 1 <= n_nodes: a staged (zero) node
+    }
+}
+
+int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack)
+{
+    iso_grid *g = const_cast<iso_grid *>(model_pack);   // a cache inside the handle; callers hold the context lock
+    if (g->d_pair) return ISO_OK;
+    ISO_REQUIRE(ctx, g->dev.ndim == 3 && g->dev.ncols == ISO_MP_NCOLS, "pair pack: not a model pack");
+    IsoDeviceGuard guard(g->device);
+    const size_t bytes = (size_t)(g->dev.n_nodes + ISO_PAD_NODES) * ISO_PP_STRIDE * sizeof(double);
+    double *d = nullptr;
+    ISO_CUDA(ctx, cudaMalloc(&d, bytes));
+    iso_pair_pack_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(g->d_grid, g->dev.n_nodes, d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return iso_check_cuda(ctx, e, "iso_grid_pair_pack");
+    }
+    g->d_pair = d;
+    g->dev.gp = d;
+    return ISO_OK;
+}
+
 static int fill_axes(iso_ctx *ctx, iso_grid *g)
 {
     // concatenated (a[i], 1 / (a[i+1] - a[i])) table + closed-form descriptors
@@ -71,6 +107,7 @@ static void free_grid(iso_grid *g)
     if (!g) return;
     if (g->d_grid) cudaFree(g->d_grid);
     if (g->d_nodes) cudaFree(g->d_nodes);
+    if (g->d_pair) cudaFree(g->d_pair);
     delete g;
 }
 
@@ -152,6 +189,7 @@ int iso_grid_repack(iso_ctx *ctx, const iso_grid *src, const int32_t *cols, int 
     g->dev = src->dev;
     g->dev.ncols = ncols_out;
     g->dev.g = nullptr;
+    g->dev.gp = nullptr;
     g->dev.nodes = nullptr;
     for (int d = 0; d <= ISO_MAX_DIM; d++) g->shape[d] = src->shape[d];
     g->shape[src->dev.ndim] = ncols_out;

@@ -172,6 +172,10 @@ static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
 // axis tables that go to shared memory: every non-closed-form axis of the two grids
 int iso_row_grids_fill(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, IsoRowGrids *out, size_t *smem_bytes)
 {
+#if ISO_PAIR_RECORDS
+    int prc = iso_grid_pair_pack(ctx, mp);   // EEP-pair records of the model pack (built once, cached in the handle)
+    if (prc != ISO_OK) return prc;
+#endif
     out->mg = mp->dev;
     out->bg = bp->dev;
     int total = 0;

@@ -12,6 +12,10 @@
 #include "iso_common.cuh"
 #include "iso_prior.cuh"
 
+#ifndef ISO_PAIR_RECORDS
+#define ISO_PAIR_RECORDS 1   // gather the model cell as four 96-byte EEP-pair records (0: eight 64-byte nodes)
+#endif
+
 // device image of one star model (built from the public iso_model by iso_models_stage)
 struct IsoGaussDev {
     double val;   // observed value
@@ -238,6 +242,38 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                 iso_corners<3>(mg, idx, y, node, w);
 #pragma unroll
                 for (int c = 0; c < 8; c++) v[c] = 0.0;
+#if ISO_PAIR_RECORDS
+                // The two EEP-adjacent corners 2s, 2s + 1 of a cell are ONE 96-byte pair record (3 sectors instead of
+                // 4): record node[2s] holds the six always-needed columns of flat nodes node[2s] and node[2s] + 1 —
+                // the same node the reference's unchecked index arithmetic reaches for corner 2s + 1, incl. the zero
+                // padding past the array.  Accumulation stays in the reference's corner order.
+#pragma unroll
+                for (int s2 = 0; s2 < 4; s2++) {
+                    const double *rec = mg.gp + (size_t)node[2 * s2] * ISO_PP_STRIDE;
+                    const iso_d4 q0 = iso_ldg256(rec), q1 = iso_ldg256(rec + 4), q2 = iso_ldg256(rec + 8);
+                    const double wa = w[2 * s2], wb = w[2 * s2 + 1];
+                    v[0] = fma(q0.x, wa, v[0]);
+                    v[1] = fma(q0.y, wa, v[1]);
+                    v[2] = fma(q0.z, wa, v[2]);
+                    v[3] = fma(q0.w, wa, v[3]);
+                    v[4] = fma(q1.x, wa, v[4]);
+                    v[5] = fma(q1.y, wa, v[5]);
+                    v[0] = fma(q1.z, wb, v[0]);
+                    v[1] = fma(q1.w, wb, v[1]);
+                    v[2] = fma(q2.x, wb, v[2]);
+                    v[3] = fma(q2.y, wb, v[3]);
+                    v[4] = fma(q2.z, wb, v[4]);
+                    v[5] = fma(q2.w, wb, v[5]);
+                }
+                if (k == 0 && m.has_nu_max) {   // asteroseismic columns (rare): from the 8-column nodes
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double2 sv = __ldg(reinterpret_cast<const double2 *>(mg.g + (size_t)node[j] * ISO_MP_NCOLS + ISO_MP_NU_MAX));
+                        v[ISO_MP_NU_MAX] = fma(sv.x, w[j], v[ISO_MP_NU_MAX]);
+                        v[ISO_MP_DELTA_NU] = fma(sv.y, w[j], v[ISO_MP_DELTA_NU]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const double *base = mg.g + (size_t)node[j] * ISO_MP_NCOLS;
@@ -251,6 +287,7 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                     v[6] = fma(hi.z, w[j], v[6]);
                     v[7] = fma(hi.w, w[j], v[7]);
                 }
+#endif
             }
             // EEP_prior.lnpdf: BoundedPrior.lnpdf :131-140 -> Prior.pdf :54-59 -> EEP_prior._pdf :423-429
             const double eep = TRACK ? other : p[k];
