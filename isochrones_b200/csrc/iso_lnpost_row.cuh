@@ -204,7 +204,9 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
         // isochrone grids (eep_0.., age, feh, ..): p[k] are the EEPs and `other` the age (prior "age")
         double lnp_other, lnp_feh, lnp_dist, lnp_AV, lnd = 0.0;
         if (DEF) {
-            lnp_other = TRACK ? iso_broken2_lnpdf<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.mass, p[0])
+            // one log(mass) serves both Chabrier components: walkers around the break at 1 Msun diverge inside a
+            // warp, and each side would otherwise evaluate its own logarithm
+            lnp_other = TRACK ? iso_broken2_lnpdf<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW, true>(m.mass, p[0], log(p[0]))
                               : iso_leaf_lnpdf<ISO_PRIOR_FLATLOG>(m.age.self, other);
             lnp_feh = iso_leaf_lnpdf<ISO_PRIOR_FEH>(m.feh.self, feh_in);
             lnd = log(dist);   // shared by the distance prior and the distance modulus
