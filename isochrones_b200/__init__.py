@@ -6,6 +6,7 @@ CPU fallback: the compute entry points raise when ``lib/libisochrones_b200.so`` 
 """
 __version__ = "0.1.0"
 
+from .bcio import load_mist_bc_grid  # noqa: F401
 from .interp import DFInterpolator  # noqa: F401
 from .models import (EvolutionTrackInterpolator, IsochroneInterpolator, ModelGridInterpolator,  # noqa: F401
                      get_ichrone, ichrone_from_arrays)
