@@ -682,6 +682,35 @@ def main():
         barrier()
         allgather = {"ms_per_step_with_gather": ms_g / args.steps, "value_with_gather": world * BATCH * args.steps / (ms_g * 1e-3),
                      "bytes_per_rank_per_step": BATCH * 8, "collective": "ncclAllGather f64 on the compute stream"}
+        # the same exchange fused into the lnpost kernel: every rank's kernel stores its rows into every rank's
+        # receive buffer over NVLink peer mappings (no collective launch); checked once against the NCCL result
+        if world <= 8:
+            try:
+                peer = parallel.PeerGather(ctx, rank, world, BATCH, parallel.torch_allgather_bytes(dist))
+                compiled.lnpost_device(d_post[0], BATCH, d_out)
+                comm.allgather(d_out, BATCH, d_all)
+                want = np.empty(world * BATCH)
+                ctx.d2h(want, d_all)
+                got = np.empty(world * BATCH)
+                ctx.d2h(got, peer.lnpost(compiled, d_post[0], BATCH))
+                same = bool(np.array_equal(got, want, equal_nan=True))
+                for s in range(3):
+                    peer.lnpost(compiled, d_post[s % N_BATCHES], BATCH)
+                ctx.sync()
+                barrier()
+                ctx.timer_start()
+                for s in range(args.steps):
+                    peer.lnpost(compiled, d_post[s % N_BATCHES], BATCH)
+                ms_p = max_over_ranks(ctx.timer_stop())
+                barrier()
+                allgather["fused_peer_store"] = {
+                    "ms_per_step": ms_p / args.steps, "value": world * BATCH * args.steps / (ms_p * 1e-3),
+                    "identical_to_nccl": same,
+                    "how": "iso_lnpost_allgather_device: the lnpost kernel writes each row to all ranks' buffers through "
+                           "CUDA-IPC peer mappings (NVLink), then a flag exchange; no NCCL call in the step"}
+                peer.close()
+            except Exception as e:   # e.g. CUDA IPC not permitted in this container
+                allgather["fused_peer_store"] = {"unavailable": repr(e)[:300]}
         ctx.dev_free(d_all)
         sharded = None if args.no_extras else sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
 

@@ -244,6 +244,21 @@ int iso_nccl_destroy(iso_ctx *ctx);
 /* d_recv[nranks * n] <- concat over ranks of d_send[n]; asynchronous on the compute stream */
 int iso_allgather_f64(iso_ctx *ctx, const double *d_send, int64_t n, double *d_recv);
 
+/* Fused lnpost + all-gather over NVLink peer memory (one process per GPU, at most 8 ranks of one node): the same
+ * exchange as iso_lnpost_batch_device followed by iso_allgather_f64, but the lnpost kernel itself stores every row's
+ * result into the receive buffer of every rank through CUDA-IPC peer mappings, so no collective is launched and the
+ * transfer overlaps the evaluation.  Setup: every rank creates a group, exports 128 bytes, the launcher all-gathers
+ * them (any byte transport), every rank connects.  A step returns a pointer to this rank's gathered buffer
+ * [nranks * rows_per_rank] (rank-major; valid until the step after next: the buffers alternate by step parity). */
+typedef struct iso_peer_group iso_peer_group;
+int iso_peer_create(iso_ctx *ctx, int rank, int nranks, int64_t rows_per_rank, iso_peer_group **out);
+int iso_peer_export(iso_ctx *ctx, iso_peer_group *group, void *handle128 /* 128 bytes */);
+int iso_peer_connect(iso_ctx *ctx, iso_peer_group *group, const void *handles /* [nranks][128], rank order */);
+int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack,
+                                const iso_models *models, const int32_t *d_model_of_row, const double *d_pars,
+                                int64_t N, iso_peer_group *group, const double **d_gathered);
+int iso_peer_destroy(iso_ctx *ctx, iso_peer_group *group);
+
 #ifdef __cplusplus
 }
 #endif

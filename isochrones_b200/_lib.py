@@ -108,6 +108,11 @@ SIGNATURES = {
     "iso_nccl_unique_id": (C.c_int, [_VP]),
     "iso_nccl_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
     "iso_nccl_destroy": (C.c_int, [_VP]),
+    "iso_peer_create": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int64, C.POINTER(_VP)]),
+    "iso_peer_export": (C.c_int, [_VP, _VP, _VP]),
+    "iso_peer_connect": (C.c_int, [_VP, _VP, _VP]),
+    "iso_lnpost_allgather_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _VP, C.POINTER(_VP)]),
+    "iso_peer_destroy": (C.c_int, [_VP, _VP]),
     "iso_allgather_f64": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
 }
 

@@ -80,7 +80,18 @@ struct iso_ctx {
 int iso_set_error(iso_ctx *ctx, int code, const char *fmt, ...);
 int iso_check_cuda(iso_ctx *ctx, cudaError_t e, const char *what);
 int iso_stage_reserve(iso_ctx *ctx, int slot, int64_t dev_bytes, int64_t host_bytes);
-int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack);   // builds model_pack->d_pair if absent
+int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack);
+
+// fused lnpost + all-gather over NVLink peer mappings (iso_peer.cu / iso_lnpost.cu)
+#define ISO_MAX_PEERS 8
+struct IsoPeerTargets {
+    double *out[ISO_MAX_PEERS];   // receive buffer of every rank for this step (peer-mapped device pointers)
+    long long offset;             // this rank's block starts here in every receive buffer
+    int n;
+};
+struct iso_models;
+int iso_lnpost_launch_peers(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                            const int32_t *d_model_of_row, const double *d_pars, int64_t N, const IsoPeerTargets *peers);   // builds model_pack->d_pair if absent
 
 // Chunked, double-buffered host<->device pipeline of the host-pointer entry points: alternating chunks run
 // H2D -> kernel -> D2H on the two copy streams so the transfers of one chunk overlap the kernel of the other.

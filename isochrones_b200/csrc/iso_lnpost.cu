@@ -31,6 +31,12 @@ struct IsoLnpostArgs {
     const double *pars;        // [N, 4 + n_stars] row-major
     double *lnpost, *lnprior, *lnlike;   // [N]; lnprior / lnlike may be NULL
     long long N;
+    // fused all-gather (PEER kernels, iso_peer.cu): row i of this rank is stored at peer_out[r][peer_off + i] in the
+    // receive buffer of EVERY rank r (its own included) — plain stores over NVLink peer mappings
+    double *peer_out[ISO_MAX_PEERS];
+    long long peer_off;
+    int n_peers;
+    int pad_;
 };
 
 // Everything the kernel reads besides the grids and the rows travels in the kernel parameter block (constant
@@ -42,7 +48,7 @@ struct IsoLnpostParams {
     IsoModelDev model;   // the single model (unused in catalog mode)
 };
 
-template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK>
+template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK, bool PEER = false>
 __global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : ISO_LNPOST_MIN_BLOCKS_MULTI)
 iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 {
@@ -81,7 +87,13 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
         const IsoRowResult r = iso_lnpost_row<NSTARS, PROFILE, TRACK>(P.G, s_nodes, m, p, want_prior, want_like);
         if (want_prior) a.lnprior[i] = r.lnprior;
         if (want_like) a.lnlike[i] = r.lnlike;
-        a.lnpost[i] = r.lnpost;
+        if (PEER) {
+#pragma unroll
+            for (int q = 0; q < ISO_MAX_PEERS; q++)
+                if (q < a.n_peers) a.peer_out[q][a.peer_off + i] = r.lnpost;
+        } else {
+            a.lnpost[i] = r.lnpost;
+        }
     }
 }
 
@@ -195,7 +207,7 @@ int iso_row_grids_fill(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, Iso
 
 static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, const iso_grid *bp, const iso_models *models,
                          const int32_t *d_model_of_row, const double *d_pars, int64_t N, double *d_lnpost, double *d_lnprior,
-                         double *d_lnlike)
+                         double *d_lnlike, const IsoPeerTargets *peers = nullptr)
 {
     IsoLnpostParams P;
     size_t smem = 0;
@@ -210,17 +222,33 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     a.lnprior = d_lnprior;
     a.lnlike = d_lnlike;
     a.N = N;
+    a.n_peers = 0;
+    a.peer_off = 0;
+    a.pad_ = 0;
+    for (int q = 0; q < ISO_MAX_PEERS; q++) a.peer_out[q] = nullptr;
+    if (peers) {
+        a.n_peers = peers->n;
+        a.peer_off = peers->offset;
+        for (int q = 0; q < peers->n; q++) a.peer_out[q] = peers->out[q];
+    }
+    const bool peer = peers != nullptr;
     const bool catalog = d_model_of_row != nullptr;
     int64_t want = (N + ISO_LNPOST_THREADS - 1) / ISO_LNPOST_THREADS;
     int64_t cap = (int64_t)ctx->prop.multiProcessorCount * ISO_LNPOST_BLOCKS_PER_SM;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-#define ISO_LAUNCH4(NS, CAT, PROF, TRK)                                                                                  \
+#define ISO_LAUNCH5(NS, CAT, PROF, TRK, PEER)                                                                            \
     do {                                                                                                                 \
         if (smem > 48 * 1024)                                                                                            \
-            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT, PROF, TRK>,                                    \
+            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT, PROF, TRK, PEER>,                              \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        iso_lnpost_kernel<NS, CAT, PROF, TRK><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                              \
+        iso_lnpost_kernel<NS, CAT, PROF, TRK, PEER><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                        \
+    } while (0)
+    // the fused all-gather variants exist for the default prior profile (what samplers run)
+#define ISO_LAUNCH4(NS, CAT, PROF, TRK)                                                                                  \
+    do {                                                                                                                 \
+        if (peer && PROF == ISO_PROFILE_DEFAULT) ISO_LAUNCH5(NS, CAT, ISO_PROFILE_DEFAULT, TRK, true);                   \
+        else ISO_LAUNCH5(NS, CAT, PROF, TRK, false);                                                                     \
     } while (0)
 #define ISO_LAUNCH2(NS, TRK)                                                           \
     do {                                                                               \
@@ -234,6 +262,7 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     } while (0)
     const bool def = models->profile_default;
     const bool track = models->track;
+    if (peer && !def) return iso_set_error(ctx, ISO_E_UNSUPPORTED, "fused all-gather: only models with the default prior classes");
     switch (models->n_stars) {
     case 1:
         if (track) ISO_LAUNCH2(1, true);
@@ -245,6 +274,7 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     }
 #undef ISO_LAUNCH2
 #undef ISO_LAUNCH4
+#undef ISO_LAUNCH5
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());
     return ISO_OK;
@@ -375,6 +405,24 @@ int iso_lnpost_batch_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_
     return lnpost_launch(ctx, ctx->stream, model_pack, bc_pack, models, d_model_of_row, d_pars, N, d_lnpost, d_lnprior,
                          d_lnlike);
 }
+
+}  // extern "C"
+
+// fused lnpost + all-gather launch (called by iso_peer.cu with the peer mappings of one exchange step)
+int iso_lnpost_launch_peers(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                            const int32_t *d_model_of_row, const double *d_pars, int64_t N, const IsoPeerTargets *peers)
+{
+    int rc = iso_check_lnpost_handles(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0 && peers && peers->n >= 1 && peers->n <= ISO_MAX_PEERS, "fused all-gather: bad argument");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, d_pars, "lnpost: NULL buffer");
+    ISO_REQUIRE(ctx, d_model_of_row || models->n_models == 1, "lnpost: several models staged but no model_of_row given");
+    return lnpost_launch(ctx, ctx->stream, model_pack, bc_pack, models, d_model_of_row, d_pars, N, nullptr, nullptr, nullptr,
+                         peers);
+}
+
+extern "C" {
 
 int iso_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
                      const int32_t *h_model_of_row, const double *h_pars, int64_t N, double *h_lnpost, double *h_lnprior,

@@ -130,6 +130,49 @@ class NcclGather(object):
         _lib.lib().iso_nccl_destroy(self.ctx.handle)
 
 
+def torch_allgather_bytes(dist):
+    """``payload -> [payload of rank 0, payload of rank 1, ...]`` over an initialised ``torch.distributed`` group
+    (plumbing only: ships the 128-byte peer handles)."""
+    def allgather(payload):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, payload)
+        return out
+    return allgather
+
+
+class PeerGather(object):
+    """Fused lnpost + all-gather over NVLink peer memory (``iso_peer_*``): the lnpost kernel of every rank stores its
+    rows straight into the receive buffer of every rank, so the sampler's acceptance step needs no collective launch.
+    One process per GPU, at most 8 ranks of one node; ``rows_per_rank`` is the (padded) block every rank contributes."""
+
+    def __init__(self, ctx, rank, world, rows_per_rank, allgather_bytes):
+        self.ctx, self.rank, self.world, self.pad = ctx, int(rank), int(world), int(rows_per_rank)
+        self.handle = C.c_void_p()
+        ctx.check(_lib.lib().iso_peer_create(ctx.handle, self.rank, self.world, self.pad, C.byref(self.handle)))
+        if self.world > 1:
+            buf = C.create_string_buffer(128)
+            ctx.check(_lib.lib().iso_peer_export(ctx.handle, self.handle, buf))
+            handles = allgather_bytes(bytes(buf.raw))
+            if len(handles) != self.world or any(len(h) != 128 for h in handles):
+                raise ValueError("the handle exchange must return one 128-byte payload per rank")
+            blob = C.create_string_buffer(b"".join(handles), 128 * self.world)
+            ctx.check(_lib.lib().iso_peer_connect(ctx.handle, self.handle, blob))
+
+    def lnpost(self, compiled, d_pars, n, d_model_of_row=None):
+        """Evaluate this rank's ``n`` rows (device buffer) and return the device pointer of the gathered
+        ``[world * rows_per_rank]`` lnpost vector (rank-major); asynchronous on the context's compute stream."""
+        out = C.c_void_p()
+        self.ctx.check(_lib.lib().iso_lnpost_allgather_device(
+            self.ctx.handle, compiled.model_pack.handle, compiled.bc_pack.handle, compiled.handle, d_model_of_row, d_pars,
+            int(n), self.handle, C.byref(out)))
+        return out
+
+    def close(self):
+        if self.handle:
+            _lib.lib().iso_peer_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+
+
 def sharded_lnpost(compiled, pars, sharder, gather):
     """Evaluate this rank's block of ``pars[N, ndim]`` and all-gather the results: every rank returns ``lnpost[N]``.
 
