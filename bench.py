@@ -453,7 +453,7 @@ def extra_workloads(ctx, bc, args, peak):
     return out
 
 
-def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks):
+def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks, dist):
     """BASELINE.json configs 4 and 5 on N GPUs (every rank runs this; rank 0 reports):
     configs[4]: BinaryStarModel lnpost batch of 1e6 rows IN TOTAL, rows sharded in contiguous blocks (RowSharder), the
     per-row results all-gathered so that every rank holds the full lnpost vector (what a sampler's acceptance step
@@ -499,8 +499,19 @@ def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
     got = np.empty((world, sh.pad))
     ctx.d2h(got, d_all)
     full = sh.assemble(got)
+    ms_f, same = None, None
+    # the same step with the gather fused into the kernel (stores over NVLink peer mappings, iso_peer_*)
+    peer, _ = make_peer_group(ctx, rank, world, sh.pad, dist, max_over_ranks) if world <= 8 else (None, "")
+    if peer is not None:
+        got_f = np.empty((world, sh.pad))
+        ctx.d2h(got_f, peer.lnpost(binary.compiled, d_p, n_mine))
+        same = bool(np.array_equal(sh.assemble(got_f), full, equal_nan=True))
+        ms_f = timed(lambda: peer.lnpost(binary.compiled, d_p, n_mine))
+        peer.close()
     out["binary_1e6_rows_sharded"] = {
         "value": BATCH / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "ms_per_step_without_gather": ms_k,
+        "ms_per_step_fused_peer_store": ms_f, "value_fused_peer_store": (BATCH / (ms_f * 1e-3)) if ms_f else None,
+        "fused_identical_to_nccl": same,
         "rows_per_gpu": sh.pad, "finite_frac": float(np.isfinite(full).mean()), "scaling": "strong",
         "config": "configs[4]: BinaryStarModel, iso grid 107x15x1710, 4 bands + parallax, 1e6 rows in total sharded over "
                   "%d GPUs, ncclAllGather of lnpost (%d B per rank) inside the timed step" % (world, sh.pad * 8)}
@@ -539,8 +550,19 @@ def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
     got = np.empty((world, pad))
     ctx.d2h(got, d_all)
     total_rows = n_stars * rows_per_star
+    ms_f, same = None, None
+    peer, _ = make_peer_group(ctx, rank, world, pad, dist, max_over_ranks) if world <= 8 else (None, "")
+    if peer is not None:
+        got_f = np.empty((world, pad))
+        ctx.d2h(got_f, peer.lnpost(compiled, d_p, n_rows, d_model_of_row=d_m))
+        same = bool(all(np.array_equal(got_f[r, :ssh.counts[r] * rows_per_star], got[r, :ssh.counts[r] * rows_per_star],
+                                       equal_nan=True) for r in range(world)))
+        ms_f = timed(lambda: peer.lnpost(compiled, d_p, n_rows, d_model_of_row=d_m))
+        peer.close()
     out["catalog_10k_stars_sharded"] = {
         "value": total_rows / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "ms_per_step_without_gather": ms_k,
+        "ms_per_step_fused_peer_store": ms_f, "value_fused_peer_store": (total_rows / (ms_f * 1e-3)) if ms_f else None,
+        "fused_identical_to_nccl": same,
         "stars_per_gpu": ssh.pad, "rows_per_gpu": pad,
         "finite_frac": float(np.isfinite(np.concatenate([got[r, :ssh.counts[r] * rows_per_star] for r in range(world)])).mean()),
         "scaling": "strong",
@@ -549,6 +571,22 @@ def sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
     for d in (d_p, d_m, d_o, d_all):
         ctx.dev_free(d)
     return out
+
+
+def make_peer_group(ctx, rank, world, rows_per_rank, dist, max_over_ranks):
+    """PeerGather on every rank, or None on every rank (the ranks agree, so that nobody waits in a barrier alone)."""
+    from isochrones_b200 import parallel
+
+    peer, err = None, ""
+    try:
+        peer = parallel.PeerGather(ctx, rank, world, rows_per_rank, parallel.torch_allgather_bytes(dist))
+    except Exception as e:   # e.g. CUDA IPC not permitted in this container
+        err = repr(e)[:300]
+    if max_over_ranks(0.0 if peer is not None else 1.0) > 0.0:
+        if peer is not None:
+            peer.close()
+        return None, err or "peer setup failed on another rank"
+    return peer, ""
 
 
 def timed_device_loop(ctx, compiled, d_batches, d_out, steps, warmup, barrier=None):
@@ -685,8 +723,10 @@ def main():
         # the same exchange fused into the lnpost kernel: every rank's kernel stores its rows into every rank's
         # receive buffer over NVLink peer mappings (no collective launch); checked once against the NCCL result
         if world <= 8:
-            try:
-                peer = parallel.PeerGather(ctx, rank, world, BATCH, parallel.torch_allgather_bytes(dist))
+            peer, err = make_peer_group(ctx, rank, world, BATCH, dist, max_over_ranks)
+            if peer is None:
+                allgather["fused_peer_store"] = {"unavailable": err}
+            else:
                 compiled.lnpost_device(d_post[0], BATCH, d_out)
                 comm.allgather(d_out, BATCH, d_all)
                 want = np.empty(world * BATCH)
@@ -709,10 +749,8 @@ def main():
                     "how": "iso_lnpost_allgather_device: the lnpost kernel writes each row to all ranks' buffers through "
                            "CUDA-IPC peer mappings (NVLink), then a flag exchange; no NCCL call in the step"}
                 peer.close()
-            except Exception as e:   # e.g. CUDA IPC not permitted in this container
-                allgather["fused_peer_store"] = {"unavailable": repr(e)[:300]}
         ctx.dev_free(d_all)
-        sharded = None if args.no_extras else sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks)
+        sharded = None if args.no_extras else sharded_workloads(ctx, bc, args, rank, world, comm, barrier, max_over_ranks, dist)
 
     if rank != 0:
         if dist is not None:
