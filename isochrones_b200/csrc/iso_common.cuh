@@ -86,8 +86,11 @@ int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack);
 #define ISO_MAX_PEERS 8
 struct IsoPeerTargets {
     double *out[ISO_MAX_PEERS];   // receive buffer of every rank for this step (peer-mapped device pointers)
+    unsigned long long *flags[ISO_MAX_PEERS];   // flag array of every rank (peer-mapped)
+    unsigned long long step;      // value the last CTA publishes in slot `rank` of every flag array
+    unsigned *done;               // CTA arrival counter (own device memory, zero between launches)
     long long offset;             // this rank's block starts here in every receive buffer
-    int n;
+    int n, rank;
 };
 struct iso_models;
 int iso_lnpost_launch_peers(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,

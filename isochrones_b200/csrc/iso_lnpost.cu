@@ -36,7 +36,12 @@ struct IsoLnpostArgs {
     double *peer_out[ISO_MAX_PEERS];
     long long peer_off;
     int n_peers;
-    int pad_;
+    int peer_rank;
+    // completion signal of the fused all-gather: the last CTA to finish publishes `peer_step` in this rank's slot of
+    // every rank's flag array (release, system scope); peer_done counts finished CTAs and is reset by that CTA
+    unsigned long long *peer_flags[ISO_MAX_PEERS];
+    unsigned long long peer_step;
+    unsigned *peer_done;
 };
 
 // Everything the kernel reads besides the grids and the rows travels in the kernel parameter block (constant
@@ -93,6 +98,23 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
                 if (q < a.n_peers) a.peer_out[q][a.peer_off + i] = r.lnpost;
         } else {
             a.lnpost[i] = r.lnpost;
+        }
+    }
+    if (PEER) {
+        // every thread's peer stores are ordered before its arrival; the last CTA then raises the flags
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(a.peer_done, 1u);
+            if (ticket == gridDim.x - 1) {
+                *a.peer_done = 0;
+                __threadfence_system();
+#pragma unroll
+                for (int q = 0; q < ISO_MAX_PEERS; q++)
+                    if (q < a.n_peers)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[q] + a.peer_rank), "l"(a.peer_step)
+                                     : "memory");
+            }
         }
     }
 }
@@ -224,12 +246,23 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     a.N = N;
     a.n_peers = 0;
     a.peer_off = 0;
-    a.pad_ = 0;
-    for (int q = 0; q < ISO_MAX_PEERS; q++) a.peer_out[q] = nullptr;
+    a.peer_rank = 0;
+    a.peer_step = 0;
+    a.peer_done = nullptr;
+    for (int q = 0; q < ISO_MAX_PEERS; q++) {
+        a.peer_out[q] = nullptr;
+        a.peer_flags[q] = nullptr;
+    }
     if (peers) {
         a.n_peers = peers->n;
         a.peer_off = peers->offset;
-        for (int q = 0; q < peers->n; q++) a.peer_out[q] = peers->out[q];
+        a.peer_rank = peers->rank;
+        a.peer_step = peers->step;
+        a.peer_done = peers->done;
+        for (int q = 0; q < peers->n; q++) {
+            a.peer_out[q] = peers->out[q];
+            a.peer_flags[q] = peers->flags[q];
+        }
     }
     const bool peer = peers != nullptr;
     const bool catalog = d_model_of_row != nullptr;

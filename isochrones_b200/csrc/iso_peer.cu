@@ -4,8 +4,9 @@
 // needs.  With NCCL that is a second operation after the kernel (iso_allgather_f64); here the lnpost
 // kernel itself stores every result into the receive buffer of EVERY rank — ordinary 8-byte stores through CUDA-IPC
 // peer mappings, carried by NVLink / NVSwitch — so the transfer overlaps the evaluation row by row and no collective
-// is launched.  Completion is a flag exchange: after the kernel a rank writes the step number into its slot of every
-// peer's flag array (system-scope release), then waits until all slots of its own array show the step (acquire).
+// is launched.  Completion is a flag exchange: the last CTA of the kernel writes the step number into this rank's slot
+// of every rank's flag array (system-scope release), and a one-warp kernel then waits until all slots of the rank's own
+// array show the step (acquire).
 //
 // Receive buffers are double-buffered by step parity: a rank that has passed the wait of step s may start writing
 // step s + 1 into its peers while a slower peer still reads step s from the other buffer; it cannot reach step s + 2
@@ -21,28 +22,13 @@ struct iso_peer_group {
     unsigned long long *d_flags = nullptr;   // [nranks]         (own allocation)
     double *peer_recv[ISO_MAX_PEERS] = {nullptr};               // peer-mapped (own entry = d_recv)
     unsigned long long *peer_flags[ISO_MAX_PEERS] = {nullptr};
+    unsigned *d_done = nullptr;           // CTA arrival counter of the fused kernel
     bool connected = false;
     unsigned long long step = 0;
 };
 
-struct IsoPeerFlags {
-    unsigned long long *flags[ISO_MAX_PEERS];
-    int n, rank;
-    unsigned long long step;
-};
-
-// after the lnpost kernel (stream order): publish `step` in this rank's slot of every rank's flag array ...
-__global__ void iso_peer_signal_kernel(IsoPeerFlags f)
-{
-    __threadfence_system();   // the kernel before us has completed; order its peer stores before the flags
-    const int r = threadIdx.x;
-    if (r < f.n) {
-        unsigned long long *p = f.flags[r] + f.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(f.step) : "memory");
-    }
-}
-
-// ... and wait until every rank has published it in ours
+// the fused kernel's last CTA publishes the step number in this rank's slot of every rank's flag array (release,
+// system scope); this kernel waits until every rank has published it in ours
 __global__ void iso_peer_wait_kernel(const unsigned long long *own_flags, int n, unsigned long long step)
 {
     const int r = threadIdx.x;
@@ -56,6 +42,13 @@ __global__ void iso_peer_wait_kernel(const unsigned long long *own_flags, int n,
     __threadfence_system();
 }
 
+// a rank with no rows in a step still has to publish the step (nobody may wait for it forever)
+__global__ void iso_peer_signal_kernel(IsoPeerTargets t)
+{
+    const int r = threadIdx.x;
+    if (r < t.n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.flags[r] + t.rank), "l"(t.step) : "memory");
+}
+
 static void peer_free(iso_peer_group *g)
 {
     if (!g) return;
@@ -66,6 +59,7 @@ static void peer_free(iso_peer_group *g)
     }
     if (g->d_recv) cudaFree(g->d_recv);
     if (g->d_flags) cudaFree(g->d_flags);
+    if (g->d_done) cudaFree(g->d_done);
     delete g;
 }
 
@@ -86,6 +80,8 @@ int iso_peer_create(iso_ctx *ctx, int rank, int nranks, int64_t rows_per_rank, i
     const size_t bytes = (size_t)2 * nranks * rows_per_rank * sizeof(double);
     cudaError_t e = cudaMalloc(&g->d_recv, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_flags, sizeof(unsigned long long) * ISO_MAX_PEERS);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_done, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_done, 0, sizeof(unsigned), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_recv, 0, bytes, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_flags, 0, sizeof(unsigned long long) * ISO_MAX_PEERS, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -147,18 +143,26 @@ int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const 
     const size_t half = (size_t)(step & 1) * (size_t)g->nranks * (size_t)g->pad;
     IsoPeerTargets t;
     t.n = g->nranks;
+    t.rank = g->rank;
+    t.step = step;
+    t.done = g->d_done;
     t.offset = (long long)g->rank * g->pad;
-    for (int r = 0; r < ISO_MAX_PEERS; r++) t.out[r] = r < g->nranks ? g->peer_recv[r] + half : nullptr;
-    int rc = iso_lnpost_launch_peers(ctx, model_pack, bc_pack, models, d_model_of_row, d_pars, N, &t);
-    if (rc != ISO_OK) return rc;
-    IsoPeerFlags f;
-    f.n = g->nranks;
-    f.rank = g->rank;
-    f.step = step;
-    for (int r = 0; r < ISO_MAX_PEERS; r++) f.flags[r] = r < g->nranks ? g->peer_flags[r] : nullptr;
-    iso_peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(f);
+    for (int r = 0; r < ISO_MAX_PEERS; r++) {
+        t.out[r] = r < g->nranks ? g->peer_recv[r] + half : nullptr;
+        t.flags[r] = r < g->nranks ? g->peer_flags[r] : nullptr;
+    }
+    if (N > 0) {
+        int rc = iso_lnpost_launch_peers(ctx, model_pack, bc_pack, models, d_model_of_row, d_pars, N, &t);
+        if (rc != ISO_OK) {
+            --g->step;   // nothing was launched: the step did not happen
+            return rc;
+        }
+    } else {
+        iso_peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(t);
+        ctx->launches += 1;
+    }
     iso_peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_flags, g->nranks, step);
-    ctx->launches += 2;
+    ctx->launches += 1;
     ISO_CUDA(ctx, cudaGetLastError());
     if (d_gathered) *d_gathered = g->d_recv + half;
     return ISO_OK;

@@ -42,6 +42,8 @@ def test_single_rank_group_matches_batch_kernel():
             ctx.d2h(got, d_all)
             ctx.dev_free(d_p)
             assert np.array_equal(got[:m], mod.lnpost_batch(rows[:m]), equal_nan=True)
+        peer.lnpost(mod.compiled, None, 0)          # a step without rows still completes (the flags advance)
+        ctx.sync()
         peer.close()
     # a model with a non-default prior has no fused variant: a loud error, not a silent fallback
     from isochrones_b200.priors import GaussianPrior
