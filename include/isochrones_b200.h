@@ -108,6 +108,16 @@ int iso_interp_mags_cols(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc
                          const double *const *h_par, int64_t N, double *h_Teff, double *h_logg, double *h_feh,
                          double *h_mags);
 
+/* Device-buffer forms of the two calls above (asynchronous on the context's compute stream; every d_* is a device
+ * pointer, d_x / d_par are HOST arrays of device pointers; the column lists are host arrays): for samples that already
+ * live in HBM, e.g. the chains of the on-device sampler. */
+int iso_interp_values_device(iso_ctx *ctx, const iso_grid *grid, const double *const *d_x, int64_t N,
+                             const int32_t *icols, int ncols, double *d_out);
+int iso_interp_mags_device(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5],
+                           int i_Teff, int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands,
+                           const double *const *d_par, int64_t N, double *d_Teff, double *d_logg, double *d_feh,
+                           double *d_mags);
+
 /* interp_eeps (interp.py:488-499) over interp_eep (:502-558): (age, feh, mass) -> EEP on an evolution-track grid
  * staged as a 3-D (feh, mass, eep) iso_grid whose column i_age holds log10 age (the per-track age arrays of
  * StellarModelGrid.get_array_grids, models.py:171-205); h_lengths[n_feh * n_mass] is the number of populated EEPs

@@ -92,6 +92,9 @@ SIGNATURES = {
                                   c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
     "iso_interp_mags_cols": (C.c_int, [_VP, _VP, _VP, c_int32_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, C.c_int,
                                        C.POINTER(c_double_p), C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "iso_interp_values_device": (C.c_int, [_VP, _VP, C.POINTER(_VP), C.c_int64, c_int32_p, C.c_int, _VP]),
+    "iso_interp_mags_device": (C.c_int, [_VP, _VP, _VP, c_int32_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, C.c_int,
+                                         C.POINTER(_VP), C.c_int64, _VP, _VP, _VP, _VP]),
     "iso_interp_eeps": (C.c_int, [_VP, _VP, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "iso_prior_eval": (C.c_int, [_VP, C.POINTER(IsoPrior), C.c_int, c_double_p, C.c_int64, c_double_p]),
     "iso_models_stage": (C.c_int, [_VP, C.POINTER(IsoModel), C.c_int, C.POINTER(_VP)]),
@@ -292,6 +295,13 @@ class DeviceGrid:
         ptrs = (c_double_p * self.ndim)(*[dp(a) for a in xx])
         self.ctx.check(lib().iso_interp_values(self.ctx.handle, self.handle, ptrs, n, ip(icols), len(icols), dp(out)))
         return out
+
+    def interp_values_device(self, d_xx, n, icols, d_out):
+        """Asynchronous interpolation on device buffers: ``d_xx`` = one device pointer per axis (each ``[n]``),
+        ``d_out`` = device ``[n, len(icols)]`` (``iso_interp_values_device``)."""
+        icols = np.ascontiguousarray(icols, dtype=np.int32)
+        ptrs = (_VP * self.ndim)(*d_xx)
+        self.ctx.check(lib().iso_interp_values_device(self.ctx.handle, self.handle, ptrs, int(n), ip(icols), len(icols), d_out))
 
     def close(self):
         if self.handle:

@@ -67,6 +67,7 @@ struct iso_ctx {
     std::string last_error;
     std::recursive_mutex mu;                // entry points that touch the staging buffers / streams hold it
     int64_t launches = 0;
+    int *d_small = nullptr;                 // 1024-int scratch for the column lists of the device-buffer entry points
     // staging buffers for the host-pointer entry points (grown on demand)
     void *d_stage[2] = {nullptr, nullptr};
     int64_t d_stage_bytes[2] = {0, 0};

@@ -113,6 +113,7 @@ int iso_ctx_destroy(iso_ctx *ctx)
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->d_small) cudaFree(ctx->d_small);
     delete ctx;
     return ISO_OK;
 }

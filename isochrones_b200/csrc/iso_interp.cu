@@ -351,6 +351,84 @@ int iso_interp_mags(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, con
                                 h_logg, h_feh, h_mags);
 }
 
+// column list of a device-buffer call -> the context's scratch (stream-ordered before the kernel that reads it)
+static int small_upload(iso_ctx *ctx, const int32_t *h, int n, int offset, const int **d)
+{
+    ISO_REQUIRE(ctx, n >= 0 && offset >= 0 && offset + n <= 1024, "device entry point: too many columns");
+    if (!ctx->d_small) ISO_CUDA(ctx, cudaMalloc(&ctx->d_small, 1024 * sizeof(int)));
+    if (n > 0) ISO_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + offset, h, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    *d = ctx->d_small + offset;
+    return ISO_OK;
+}
+
+int iso_interp_values_device(iso_ctx *ctx, const iso_grid *grid, const double *const *d_x, int64_t N, const int32_t *icols,
+                             int ncols, double *d_out)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_values_device: ctx is NULL");
+    ISO_REQUIRE(ctx, grid && d_x && icols, "iso_interp_values_device: NULL argument");
+    ISO_REQUIRE(ctx, grid->device == ctx->device, "iso_interp_values_device: grid belongs to another device");
+    ISO_REQUIRE(ctx, N >= 0 && ncols >= 1, "iso_interp_values_device: bad sizes");
+    for (int c = 0; c < ncols; c++)
+        ISO_REQUIRE(ctx, icols[c] >= 0 && icols[c] < grid->dev.ncols, "iso_interp_values_device: column index out of range");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, d_out, "iso_interp_values_device: out is NULL");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    IsoDeviceGuard guard(ctx->device);
+    const int *d_cols = nullptr;
+    int rc = small_upload(ctx, icols, ncols, 0, &d_cols);
+    if (rc != ISO_OK) return rc;
+    void *d[ISO_MAX_DIM + 1];
+    for (int k = 0; k < grid->dev.ndim; k++) {
+        ISO_REQUIRE(ctx, d_x[k], "iso_interp_values_device: NULL coordinate array");
+        d[k] = const_cast<double *>(d_x[k]);
+    }
+    d[grid->dev.ndim] = d_out;
+    InterpUser u{grid, d_cols, ncols};
+    return interp_launch(ctx, ctx->stream, d, 0, N, &u);
+}
+
+int iso_interp_mags_device(iso_ctx *ctx, const iso_grid *model, const iso_grid *bc, const int32_t index_order[5], int i_Teff,
+                           int i_logg, int i_feh, int i_Mbol, const int32_t *bc_cols, int n_bands, const double *const *d_par,
+                           int64_t N, double *d_Teff, double *d_logg, double *d_feh, double *d_mags)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_interp_mags_device: ctx is NULL");
+    ISO_REQUIRE(ctx, model && bc && index_order && d_par, "iso_interp_mags_device: NULL argument");
+    ISO_REQUIRE(ctx, model->device == ctx->device && bc->device == ctx->device, "iso_interp_mags_device: grid on another device");
+    ISO_REQUIRE(ctx, model->dev.ndim == 3 && bc->dev.ndim == 4, "iso_interp_mags_device: model grid must be 3-D, BC grid 4-D");
+    ISO_REQUIRE(ctx, N >= 0 && n_bands >= 0 && (n_bands == 0 || bc_cols), "iso_interp_mags_device: bad sizes");
+    int mc = model->dev.ncols;
+    ISO_REQUIRE(ctx, i_Teff >= 0 && i_Teff < mc && i_logg >= 0 && i_logg < mc && i_feh >= 0 && i_feh < mc && i_Mbol >= 0 &&
+                         i_Mbol < mc, "iso_interp_mags_device: model column index out of range");
+    for (int b = 0; b < n_bands; b++)
+        ISO_REQUIRE(ctx, bc_cols[b] >= 0 && bc_cols[b] < bc->dev.ncols, "iso_interp_mags_device: band column out of range");
+    for (int j = 0; j < 5; j++)
+        ISO_REQUIRE(ctx, index_order[j] >= 0 && index_order[j] < 5 && d_par[j], "iso_interp_mags_device: bad index_order / NULL array");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, d_Teff && d_logg && d_feh && (n_bands == 0 || d_mags), "iso_interp_mags_device: NULL buffer");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    IsoDeviceGuard guard(ctx->device);
+    const int *d_cols = nullptr;
+    int rc = small_upload(ctx, bc_cols, n_bands, 512, &d_cols);
+    if (rc != ISO_OK) return rc;
+    MagsUser u;
+    u.model = model;
+    u.bc = bc;
+    for (int j = 0; j < 5; j++) u.proto.index_order[j] = index_order[j];
+    u.proto.i_Teff = i_Teff;
+    u.proto.i_logg = i_logg;
+    u.proto.i_feh = i_feh;
+    u.proto.i_Mbol = i_Mbol;
+    u.proto.bc_cols = d_cols;
+    u.proto.n_bands = n_bands;
+    void *d[9];
+    for (int j = 0; j < 5; j++) d[j] = const_cast<double *>(d_par[j]);
+    d[5] = d_Teff;
+    d[6] = d_logg;
+    d[7] = d_feh;
+    d[8] = d_mags;
+    return mags_launch(ctx, ctx->stream, d, 0, N, &u);
+}
+
 int iso_interp_eeps(iso_ctx *ctx, const iso_grid *track_grid, int i_age, const int32_t *h_lengths, const double *h_age,
                     const double *h_feh, const double *h_mass, int64_t N, double *h_eep)
 {

@@ -252,6 +252,18 @@ class ModelGridInterpolator(object):
             return float(teff[0]), float(logg[0]), float(feh[0]), mags[0]
         return teff, logg, feh, mags
 
+    def interp_mag_device(self, d_pars, n, bands, d_Teff, d_logg, d_feh, d_mags):
+        """``interp_mag`` on device buffers (asynchronous): ``d_pars`` = five device pointers (``param_names`` order,
+        each ``[n]``), outputs device ``[n]``, ``[n]``, ``[n]``, ``[n, len(bands)]`` (``iso_interp_mags_device``)."""
+        bands = list(bands)
+        bc = self.bc_pack(bands)
+        io = np.array(self.param_index_order, dtype=np.int32)
+        bc_cols = np.arange(len(bands), dtype=np.int32)
+        ptrs = (C.c_void_p * 5)(*d_pars)
+        self.ctx.check(_lib.lib().iso_interp_mags_device(
+            self.ctx.handle, self.model_pack.handle, bc.handle, _lib.ip(io), 0, 1, 2, 3, _lib.ip(bc_cols), len(bands), ptrs,
+            int(n), d_Teff, d_logg, d_feh, d_mags))
+
     def get_eep(self, mass, age, feh, accurate=False, **kwargs):
         """EEP of a star of given (mass, log10 age, feh) on an evolution-track grid (models.py:501-542): the fast
         bracketing interpolation ``interp_eep(s)`` (interp.py:488-558) on the GPU (``iso_interp_eeps``).  Scalars give

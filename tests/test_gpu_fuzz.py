@@ -151,3 +151,44 @@ def test_packed_and_column_entry_points_agree():
     mixed = ic.interp_mag([rows[:, 0].copy(), rows[:, 1].copy(), 0.0, 100.0, 0.1], bands)
     want = ic.interp_mag([rows[:, 0].copy(), rows[:, 1].copy(), np.zeros(n), np.full(n, 100.0), np.full(n, 0.1)], bands)
     assert np.array_equal(mixed[3], want[3], equal_nan=True)
+
+
+def test_device_buffer_interpolation_entry_points():
+    """iso_interp_values_device / iso_interp_mags_device (inputs and outputs in HBM) == the host-pointer calls."""
+    import isochrones_b200 as ib
+    from isochrones_b200 import _lib, synthetic as syn
+
+    ctx = _lib.default_context()
+    trk = syn.make_track_grid(n_feh=6, n_mass=24, n_eep=171)
+    bc = syn.make_bc_grid(bands=("V", "J", "H", "K"), n_teff=24, n_logg=10, n_feh=8, n_av=7)
+    ic = ib.ichrone_from_arrays("track", trk, bc, ctx=ctx)
+    truth = syn.default_truth("track", n_eep=171)
+    rows = syn.posterior_like_batch("track", 7001, truth, n_eep=171, seed=11)
+    rows[::37, 0] = 1e6
+    n = len(rows)
+    cols = [np.ascontiguousarray(rows[:, j]) for j in range(5)]
+    d_cols = []
+    for c in cols:
+        d = ctx.dev_alloc(c.nbytes)
+        ctx.h2d(d, c)
+        d_cols.append(d)
+    bands = ["V", "J", "H", "K"]
+    want = ic.interp_mag(cols, bands)
+    d_out = [ctx.dev_alloc(n * 8) for _ in range(3)] + [ctx.dev_alloc(n * 8 * 4)]
+    ic.interp_mag_device(d_cols, n, bands, *d_out)
+    for w, d in zip(want, d_out):
+        got = np.empty_like(w)
+        ctx.d2h(got, d)
+        assert np.array_equal(got, w, equal_nan=True)
+    # interp_value on the model grid: axes order (feh, mass, eep) = parameters (2, 0, 1)
+    props = ["Teff", "radius", "age"]
+    grid = ic.model_grid.interp
+    icols = [grid.column_index[p] for p in props]
+    want_v = grid([cols[2], cols[0], cols[1]], props)
+    d_v = ctx.dev_alloc(n * 8 * len(props))
+    grid.device_grid.interp_values_device([d_cols[2], d_cols[0], d_cols[1]], n, icols, d_v)
+    got_v = np.empty_like(want_v)
+    ctx.d2h(got_v, d_v)
+    assert np.array_equal(got_v, want_v, equal_nan=True)
+    for d in d_cols + d_out + [d_v]:
+        ctx.dev_free(d)
