@@ -61,12 +61,25 @@ def build_workload(ctx=None, small=False):
     return trk, bc, ic, truth, n_eep
 
 
-def truth_mags(trk, bc, truth):
-    """Observed magnitudes = model magnitudes at the truth (computed with the oracle so that both arms share them)."""
+def truth_mags(ic, truth):
+    """Observed magnitudes of the b200 arm = model magnitudes at the truth, rounded to 1 mmag (the product's own
+    ``interp_mag``; the reference arm derives the same numbers from the oracle, see ``oracle_truth_mags``)."""
+    _, _, _, mags = ic.interp_mag(list(truth), list(BANDS))
+    return [float(np.round(m, 3)) for m in mags]
+
+
+def oracle_grids(trk, bc):
+    """Oracle views of the two grids (CPU arm / cpu_baseline leg only)."""
     from oracle import oracle
 
-    mg = oracle.Grid(trk["grid"], trk["axes"])
-    bg = oracle.Grid(bc["grid"], bc["axes"])
+    return oracle.Grid(trk["grid"], trk["axes"]), oracle.Grid(bc["grid"], bc["axes"])
+
+
+def oracle_truth_mags(trk, bc, truth):
+    """The same observed magnitudes computed on the CPU (reference arm: no GPU is touched there)."""
+    from oracle import oracle
+
+    mg, bg = oracle_grids(trk, bc)
     ci = {c: i for i, c in enumerate(trk["columns"])}
     _, _, _, mags = oracle.interp_mags(np.asarray(truth).reshape(5, 1), [2, 0, 1, 3, 4], mg, ci["Teff"], ci["logg"],
                                        ci["feh"], ci["Mbol"], bg, list(range(len(BANDS))))
@@ -210,11 +223,12 @@ class ClockSampler(object):
                 "window": "samples inside the device-timed loop and the end-to-end loop only"}
 
 
-def cpu_baseline(trk, bc, ic_host_model, mg, bg, seed, budget_s=12.0):
+def cpu_baseline(trk, bc, ic_host_model, seed, budget_s=12.0):
     """The C port of the reference's CPU path (oracle/) on the host cores: bounded sample of the same workload."""
     from isochrones_b200 import synthetic as syn
     from oracle import oracle
 
+    mg, bg = oracle_grids(trk, bc)
     om = oracle.StarModel(ic_host_model, model_grid=mg, bc_grid=bg)
     threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     truth = syn.default_truth("track", n_eep=len(trk["axes"][2]))
@@ -241,7 +255,7 @@ def run_reference(args, rank, world):
     from oracle import oracle
 
     trk, bc, ic, truth, n_eep = build_workload(ctx=None)
-    mags, mg, bg = truth_mags(trk, bc, truth)
+    mags, mg, bg = oracle_truth_mags(trk, bc, truth)
     mod = make_model(ic, mags)
     om = oracle.StarModel(mod, model_grid=mg, bc_grid=bg)
     threads = host_threads()   # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
@@ -639,7 +653,7 @@ def main():
     numa_cpus = parallel.bind_to_gpu_numa(local_rank) if world > 1 else None   # before any pinned allocation
     ctx = _lib.default_context(local_rank)
     trk, bc, ic, truth, n_eep = build_workload(ctx=ctx, small=args.small)
-    mags, mg, bg = truth_mags(trk, bc, truth)
+    mags = truth_mags(ic, truth)
     mod = make_model(ic, mags)
     compiled = mod.compiled
     bounds = [mod.bounds(p) for p in mod.param_names]
@@ -839,7 +853,7 @@ def main():
     if allgather:
         line["allgather"] = allgather
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(trk, bc, mod, mg, bg, seed=900)
+        line["cpu_baseline"] = cpu_baseline(trk, bc, mod, seed=900)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

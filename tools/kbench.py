@@ -23,7 +23,7 @@ def main():
 
     ctx = _lib.default_context(0)
     trk, bc, ic, truth, n_eep = bench.build_workload(ctx=ctx)
-    mags, mg, bg = bench.truth_mags(trk, bc, truth)
+    mags = bench.truth_mags(ic, truth)
     mod = bench.make_model(ic, mags)
     compiled = mod.compiled
     bounds = [mod.bounds(p) for p in mod.param_names]
