@@ -67,8 +67,12 @@ __device__ __forceinline__ double iso_u01(unsigned hi, unsigned lo)
     return (double)((((unsigned long long)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
 }
 
-template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK>
-__global__ void __launch_bounds__(512, 1) iso_sampler_kernel(const __grid_constant__ IsoSamplerParams P)
+// BOUNDS = 512: ensembles of up to 1024 walkers, 128 registers per thread, several CTAs per SM (many chains in flight);
+// BOUNDS = 128: ensembles of up to 256 walkers when the chains do not fill the GPU anyway — one chain is bound by the
+// dependent latency of a single row, and with 254 registers the compiler keeps more of a row's independent work in
+// flight (a 256 x 2000 run: 29 ms instead of 33 ms).
+template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK, int BOUNDS>
+__global__ void __launch_bounds__(BOUNDS, 1) iso_sampler_kernel(const __grid_constant__ IsoSamplerParams P)
 {
     constexpr int NDIMP = NSTARS + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -249,15 +253,22 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     P.lnprob_out = d_lp;
     P.accepted = s->d_acc;
     int threads = ((s->n_walkers / 2 + 31) / 32) * 32;
+    // few chains of small ensembles: the latency-optimised instantiation (see the kernel's comment)
+    const bool few_small = threads <= 128 && s->n_chains <= ctx->prop.multiProcessorCount;
     const bool catalog = s->models->n_models > 1;
     const bool def = s->models->profile_default, track = s->models->track;
     cudaError_t e = cudaSuccess;
-#define ISO_SLAUNCH4(NS, CAT, PROF, TRK)                                                                               \
+#define ISO_SLAUNCH5(NS, CAT, PROF, TRK, BND)                                                                          \
     do {                                                                                                              \
         if (smem > 48 * 1024)                                                                                         \
-            e = cudaFuncSetAttribute(iso_sampler_kernel<NS, CAT, PROF, TRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem);                                                                      \
-        if (e == cudaSuccess) iso_sampler_kernel<NS, CAT, PROF, TRK><<<s->n_chains, threads, smem, ctx->stream>>>(P);  \
+            e = cudaFuncSetAttribute(iso_sampler_kernel<NS, CAT, PROF, TRK, BND>,                                     \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+        if (e == cudaSuccess) iso_sampler_kernel<NS, CAT, PROF, TRK, BND><<<s->n_chains, threads, smem, ctx->stream>>>(P); \
+    } while (0)
+#define ISO_SLAUNCH4(NS, CAT, PROF, TRK)                                        \
+    do {                                                                       \
+        if (few_small) ISO_SLAUNCH5(NS, CAT, PROF, TRK, 128);                  \
+        else ISO_SLAUNCH5(NS, CAT, PROF, TRK, 512);                            \
     } while (0)
 #define ISO_SLAUNCH2(NS, TRK)                                                    \
     do {                                                                         \
@@ -279,6 +290,7 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     }
 #undef ISO_SLAUNCH2
 #undef ISO_SLAUNCH4
+#undef ISO_SLAUNCH5
     ctx->launches++;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess && d_chain)
