@@ -257,10 +257,22 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         return ISO_OK;
     };
 
+    // Chunk schedule: full chunks while more than one chunk of rows remains, then halves of what is left (down to
+    // ISO_PIPE_TAIL_ROWS): the transfers are the bottleneck, and whatever the LAST chunk's kernel and result copy take
+    // cannot overlap anything — so the last chunk is made small.
+    static const int64_t tail_rows = [] {
+        const char *e = getenv("ISO_PIPE_TAIL_ROWS");
+        long long v = e ? atoll(e) : 0;
+        return (int64_t)(v >= 1024 ? v : 16384);
+    }();
     int c = 0;
-    for (int64_t row0 = 0; row0 < n_rows; row0 += chunk, c++) {
+    int64_t n = 0;
+    for (int64_t row0 = 0; row0 < n_rows; row0 += n, c++) {
         int s = c & (n_slots - 1);
-        int64_t n = n_rows - row0 < chunk ? n_rows - row0 : chunk;
+        const int64_t left = n_rows - row0;
+        if (left > chunk) n = chunk;
+        else if (left > 2 * tail_rows && n_rows > chunk) n = (left / 2 + 4095) & ~(int64_t)4095;
+        else n = left;
         int rc = finalize(s);
         if (rc != ISO_OK) return rc;
         cudaStream_t st = ctx->copy_stream[s];
