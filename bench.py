@@ -338,6 +338,33 @@ def interp_workloads(ctx, ic, truth, n_eep, args, mod=None):
             "value": 128.0 / dt, "unit": UNIT, "us_per_call": dt * 1e6,
             "config": "BasicStarModel.lnpost_batch on a pageable [128, 5] array: what a host-driven emcee (vectorize=True) "
                       "pays per half-step of a 256-walker ensemble"}
+    # the two interpolation kernels alone (device-resident inputs and outputs, CUDA events)
+    d_x = []
+    for j in range(5):
+        d = ctx.dev_alloc(BATCH * 8)
+        ctx.h2d(d, np.ascontiguousarray(pts[:, j]))
+        d_x.append(d)
+    grid = ic.model_grid.interp
+    icols = [grid.column_index[c] for c in props]
+    d_v = ctx.dev_alloc(BATCH * 8 * len(props))
+    d_m = [ctx.dev_alloc(BATCH * 8) for _ in range(3)] + [ctx.dev_alloc(BATCH * 8 * len(BANDS))]
+    for name, fn, b_alg in (
+            ("interp_value_3_props_device", lambda: grid.device_grid.interp_values_device([d_x[2], d_x[0], d_x[1]], BATCH, icols, d_v),
+             8.0 * (3 + 8 * 3 + 3)),
+            ("interp_mag_4_bands_device", lambda: ic.interp_mag_device(d_x, BATCH, list(BANDS), *d_m),
+             8.0 * (5 + 8 * 4 + 16 * len(BANDS) + 3 + len(BANDS)))):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            fn()
+        k_ms = ctx.timer_stop() / args.steps
+        out[name] = {"value": BATCH / (k_ms * 1e-3), "unit": "points/s", "ms_per_step": k_ms,
+                     "algorithmic_bytes_per_point": b_alg, "achieved_gb_s": b_alg * BATCH / (k_ms * 1e-3) / 1e9,
+                     "config": "kernel only: inputs and outputs in HBM (iso_%s)" % ("interp_values_device" if "value" in name else "interp_mags_device")}
+    for d in d_x + d_m + [d_v]:
+        ctx.dev_free(d)
     outs = (ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)), ctx.pinned_empty((BATCH,)),
             ctx.pinned_empty((BATCH, len(BANDS))))
     for _ in range(3):
