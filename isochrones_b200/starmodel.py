@@ -11,6 +11,7 @@ them.  Priors the device cannot evaluate raise at compile time — there is no C
 Out of scope: ini parsing, HDF save/load, corner plots, the obs-tree ``StarModel``.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -32,6 +33,27 @@ class CompiledModel(object):
         arr = (_lib.IsoModel * len(structs))(*structs)
         self.handle = C.c_void_p()
         self.ctx.check(_lib.lib().iso_models_stage(self.ctx.handle, arr, len(structs), C.byref(self.handle)))
+        self._one = threading.local()   # per-thread buffers of the scalar call
+
+    def lnpost_one(self, p):
+        """``lnpost`` of ONE parameter vector — the reference's scalar interface, as a sampler calls it millions of
+        times.  The row and the result live in small page-locked buffers (one pair per host thread) whose ctypes
+        pointers are cached, so the call is: five stores, one C call (kernel reads / writes the pinned buffers
+        directly: the library's small-call path), one load."""
+        one = self._one
+        buf = getattr(one, "buf", None)
+        if buf is None:
+            if self.n_models != 1:
+                raise ValueError("model_of_row is required when several models are compiled together")
+            h_in, h_out = self.ctx.pinned_empty((1, self.ndim)), self.ctx.pinned_empty((1,))
+            buf = one.buf = (h_in, h_out, _lib.dp(h_in), _lib.dp(h_out), _lib.lib().iso_lnpost_batch, self.ctx.handle,
+                             self.model_pack.handle, self.bc_pack.handle)
+        h_in, h_out, p_in, p_out, fn, ctxh, mph, bph = buf
+        h_in[0, :] = p          # raises on a wrong length
+        rc = fn(ctxh, mph, bph, self.handle, None, p_in, 1, p_out, None, None)
+        if rc:
+            self.ctx.check(rc)
+        return float(h_out[0])
 
     def lnpost(self, pars, parts=False, model_of_row=None, out=None):
         """``pars[N, ndim]`` -> ``lnpost[N]`` (and ``lnprior[N]``, ``lnlike[N]`` when ``parts``)."""
@@ -283,7 +305,7 @@ class BasicStarModel(object):
 
     def lnpost(self, p, **kwargs):
         """``lnprior + lnlike`` with ``-inf`` when the prior is not finite (starmodel.py:538-542)."""
-        return float(self.compiled.lnpost(self._row(p))[0])
+        return self.compiled.lnpost_one(p)
 
     def mnest_prior(self, cube, ndim=None, nparams=None):
         """Unit cube -> parameter box, in place (starmodel.py:1637-1640); ``cube`` may be ``[ndim]`` or ``[N, ndim]``."""
