@@ -98,6 +98,7 @@ def load_mist_bc_grid(datadir, bands, Rv=3.1):
     system the bands need): ``{"grid": [nT, ng, nf, nA, n_bands], "axes": (Teff, logg, [Fe/H], Av), "columns": bands,
     "kind": "bc"}`` — the dict ``ichrone_from_arrays`` / ``BCGrid`` take."""
     bands = list(bands)
+    datadir = os.path.expanduser(datadir)
     wanted = {}
     for b in bands:
         phot, col = mist_band(b)
