@@ -35,24 +35,29 @@ class CompiledModel(object):
         self.ctx.check(_lib.lib().iso_models_stage(self.ctx.handle, arr, len(structs), C.byref(self.handle)))
         self._one = threading.local()   # per-thread buffers of the scalar call
 
-    def lnpost_one(self, p):
+    def lnpost_one(self, p, parts=False):
         """``lnpost`` of ONE parameter vector — the reference's scalar interface, as a sampler calls it millions of
-        times.  The row and the result live in small page-locked buffers (one pair per host thread) whose ctypes
-        pointers are cached, so the call is: five stores, one C call (kernel reads / writes the pinned buffers
-        directly: the library's small-call path), one load."""
+        times (``parts``: the ``(lnpost, lnprior, lnlike)`` triple instead).  The row and the results live in small
+        page-locked buffers (one set per host thread) whose ctypes pointers are cached, so the call is: five stores,
+        one C call (kernel reads / writes the pinned buffers directly: the library's small-call path), one load."""
         one = self._one
         buf = getattr(one, "buf", None)
         if buf is None:
             if self.n_models != 1:
                 raise ValueError("model_of_row is required when several models are compiled together")
-            h_in, h_out = self.ctx.pinned_empty((1, self.ndim)), self.ctx.pinned_empty((1,))
-            buf = one.buf = (h_in, h_out, _lib.dp(h_in), _lib.dp(h_out), _lib.lib().iso_lnpost_batch, self.ctx.handle,
-                             self.model_pack.handle, self.bc_pack.handle)
-        h_in, h_out, p_in, p_out, fn, ctxh, mph, bph = buf
+            h_in, h_out = self.ctx.pinned_empty((1, self.ndim)), self.ctx.pinned_empty((3,))
+            buf = one.buf = (h_in, h_out, _lib.dp(h_in), _lib.dp(h_out[0:1]), _lib.dp(h_out[1:2]), _lib.dp(h_out[2:3]),
+                             _lib.lib().iso_lnpost_batch, self.ctx.handle, self.model_pack.handle, self.bc_pack.handle)
+        h_in, h_out, p_in, p_post, p_prior, p_like, fn, ctxh, mph, bph = buf
         h_in[0, :] = p          # raises on a wrong length
-        rc = fn(ctxh, mph, bph, self.handle, None, p_in, 1, p_out, None, None)
+        if parts:
+            rc = fn(ctxh, mph, bph, self.handle, None, p_in, 1, p_post, p_prior, p_like)
+        else:
+            rc = fn(ctxh, mph, bph, self.handle, None, p_in, 1, p_post, None, None)
         if rc:
             self.ctx.check(rc)
+        if parts:
+            return float(h_out[0]), float(h_out[1]), float(h_out[2])
         return float(h_out[0])
 
     def lnpost(self, pars, parts=False, model_of_row=None, out=None):
@@ -281,12 +286,6 @@ class BasicStarModel(object):
         return self._compiled
 
     # ---- the hot path ------------------------------------------------------------------------------------------
-    def _row(self, pars):
-        p = np.asarray(pars, dtype=np.float64).reshape(1, -1)
-        if p.shape[1] != self.n_params:
-            raise ValueError("expected %d parameters" % self.n_params)
-        return p
-
     def lnpost_batch(self, pars, parts=False, out=None):
         """Batched ``lnpost`` over rows of ``pars[N, n_params]`` — one fused kernel launch per chunk."""
         return self.compiled.lnpost(pars, parts=parts, out=out)
@@ -298,10 +297,10 @@ class BasicStarModel(object):
         return self.compiled.lnpost(pars, parts=True)[2]
 
     def lnlike(self, pars):
-        return float(self.compiled.lnpost(self._row(pars), parts=True)[2][0])
+        return self.compiled.lnpost_one(pars, parts=True)[2]
 
     def lnprior(self, pars):
-        return float(self.compiled.lnpost(self._row(pars), parts=True)[1][0])
+        return self.compiled.lnpost_one(pars, parts=True)[1]
 
     def lnpost(self, p, **kwargs):
         """``lnprior + lnlike`` with ``-inf`` when the prior is not finite (starmodel.py:538-542)."""
