@@ -22,6 +22,16 @@
 // EEP-adjacent corners of a cell — in 96 bytes = 3 sectors, instead of 2 x 64-byte nodes = 4 sectors.
 #define ISO_PP_NCOLS 6
 #define ISO_PP_STRIDE 12
+// Layouts of the model cell the fused row kernels can gather (all hold the same numbers; a batch picks one):
+//   ISO_LAYOUT_NODE64 — the 8-column model pack itself: 8 corners x one 64-byte node (16 sectors per cell, 64 B/node);
+//   ISO_LAYOUT_PAIR96 — EEP-pair records: 4 x 96 bytes (12 sectors per cell, 96 B/node: every node stored twice);
+//   ISO_LAYOUT_NODE48 — the six always-needed columns, 48 bytes per node, no duplication: the two EEP-adjacent nodes
+//       of a corner pair are 96 contiguous bytes at a 16-byte-aligned offset = 3 or 4 sectors (14 per cell on
+//       average, 48 B/node: the smallest footprint, for batches whose gathers spread beyond the L2).
+#define ISO_LAYOUT_NODE64 0
+#define ISO_LAYOUT_PAIR96 1
+#define ISO_LAYOUT_NODE48 2
+#define ISO_N48_PAD_NODES 4   // zero nodes behind the 48-byte-node array (node r + 1 and the 16-byte overhang of an odd pair)
 
 // ------------------------------------------------------------------------------------------------
 // host-side objects behind the opaque handles
@@ -38,6 +48,7 @@ struct IsoAxisDev {
 struct IsoGridDev {     // by-value kernel argument
     const double *g;    // [n_nodes + ISO_PAD_NODES][ncols]
     const double *gp;   // model packs only: EEP-pair records [n_nodes + ISO_PAD_NODES][ISO_PP_STRIDE] (or NULL)
+    const double *g48;  // model packs only: 48-byte nodes [n_nodes + ISO_N48_PAD_NODES][ISO_PP_NCOLS] (or NULL)
     const double2 *nodes;   // concatenated axis tables
     long long n_nodes;
     int ndim, ncols;
@@ -52,10 +63,14 @@ struct iso_grid {
     double *d_grid = nullptr;
     double2 *d_nodes = nullptr;
     double *d_pair = nullptr;               // EEP-pair records, built on first use by a row kernel (iso_grid_pair_pack)
+    double *d_n48 = nullptr;                // 48-byte nodes, built on first use (iso_grid_n48_pack)
     std::vector<double> h_axes[ISO_MAX_DIM];
     int64_t shape[ISO_MAX_DIM + 1];
     int device = 0;
 };
+
+#define ISO_CLAIM_SLOTS 3
+#define ISO_CLAIM_STRIDE 16   // unsigned long long per slot: [0] next unclaimed row, [1] finished CTAs
 
 struct iso_ctx {
     int device = 0;
@@ -68,6 +83,9 @@ struct iso_ctx {
     std::recursive_mutex mu;                // entry points that touch the staging buffers / streams hold it
     int64_t launches = 0;
     int *d_small = nullptr;                 // 1024-int scratch for the column lists of the device-buffer entry points
+    // row-claim counters of the dynamically scheduled lnpost kernels: per stream slot (compute stream, copy streams)
+    // one (claim, done) pair, 128 bytes apart; zero between launches (the last CTA of a launch resets its pair)
+    unsigned long long *d_claim = nullptr;
     // staging buffers for the host-pointer entry points (grown on demand)
     void *d_stage[2] = {nullptr, nullptr};
     int64_t d_stage_bytes[2] = {0, 0};
@@ -82,6 +100,7 @@ int iso_set_error(iso_ctx *ctx, int code, const char *fmt, ...);
 int iso_check_cuda(iso_ctx *ctx, cudaError_t e, const char *what);
 int iso_stage_reserve(iso_ctx *ctx, int slot, int64_t dev_bytes, int64_t host_bytes);
 int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack);
+int iso_grid_n48_pack(iso_ctx *ctx, const iso_grid *model_pack);
 
 // fused lnpost + all-gather over NVLink peer mappings (iso_peer.cu / iso_lnpost.cu)
 #define ISO_MAX_PEERS 8

@@ -92,6 +92,8 @@ int iso_ctx_create(int device, iso_ctx **out)
     }
     CTX_TRY(cudaEventCreate(&ctx->ev_start));
     CTX_TRY(cudaEventCreate(&ctx->ev_stop));
+    CTX_TRY(cudaMalloc(&ctx->d_claim, ISO_CLAIM_SLOTS * ISO_CLAIM_STRIDE * sizeof(unsigned long long)));
+    CTX_TRY(cudaMemset(ctx->d_claim, 0, ISO_CLAIM_SLOTS * ISO_CLAIM_STRIDE * sizeof(unsigned long long)));
 #undef CTX_TRY
     *out = ctx;
     return ISO_OK;
@@ -114,6 +116,7 @@ int iso_ctx_destroy(iso_ctx *ctx)
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->d_claim) cudaFree(ctx->d_claim);
     delete ctx;
     return ISO_OK;
 }

@@ -62,6 +62,39 @@ int iso_grid_pair_pack(iso_ctx *ctx, const iso_grid *model_pack)
     return ISO_OK;
 }
 
+// 48-byte nodes of an 8-column model pack: columns 0..5 of every node, followed by ISO_N48_PAD_NODES zero nodes
+__global__ void iso_n48_pack_kernel(const double *__restrict__ src, long long n_nodes, double *__restrict__ dst)
+{
+    const long long total = (n_nodes + ISO_N48_PAD_NODES) * (long long)ISO_PP_NCOLS;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long node = t / ISO_PP_NCOLS;
+        const int c = (int)(t - node * ISO_PP_NCOLS);
+        dst[t] = node < n_nodes ? src[node * ISO_MP_NCOLS + c] : 0.0;
+    }
+}
+
+int iso_grid_n48_pack(iso_ctx *ctx, const iso_grid *model_pack)
+{
+    iso_grid *g = const_cast<iso_grid *>(model_pack);   // a cache inside the handle; callers hold the context lock
+    if (g->d_n48) return ISO_OK;
+    ISO_REQUIRE(ctx, g->dev.ndim == 3 && g->dev.ncols == ISO_MP_NCOLS, "48-byte node pack: not a model pack");
+    IsoDeviceGuard guard(g->device);
+    const size_t bytes = (size_t)(g->dev.n_nodes + ISO_N48_PAD_NODES) * ISO_PP_NCOLS * sizeof(double);
+    double *d = nullptr;
+    ISO_CUDA(ctx, cudaMalloc(&d, bytes));
+    iso_n48_pack_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(g->d_grid, g->dev.n_nodes, d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return iso_check_cuda(ctx, e, "iso_grid_n48_pack");
+    }
+    g->d_n48 = d;
+    g->dev.g48 = d;
+    return ISO_OK;
+}
+
 static int fill_axes(iso_ctx *ctx, iso_grid *g)
 {
     // concatenated (a[i], 1 / (a[i+1] - a[i])) table + closed-form descriptors
@@ -108,6 +141,7 @@ static void free_grid(iso_grid *g)
     if (g->d_grid) cudaFree(g->d_grid);
     if (g->d_nodes) cudaFree(g->d_nodes);
     if (g->d_pair) cudaFree(g->d_pair);
+    if (g->d_n48) cudaFree(g->d_n48);
     delete g;
 }
 
@@ -190,6 +224,7 @@ int iso_grid_repack(iso_ctx *ctx, const iso_grid *src, const int32_t *cols, int 
     g->dev.ncols = ncols_out;
     g->dev.g = nullptr;
     g->dev.gp = nullptr;
+    g->dev.g48 = nullptr;
     g->dev.nodes = nullptr;
     for (int d = 0; d <= ISO_MAX_DIM; d++) g->shape[d] = src->shape[d];
     g->shape[src->dev.ndim] = ncols_out;

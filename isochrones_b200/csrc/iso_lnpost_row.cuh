@@ -12,8 +12,8 @@
 #include "iso_common.cuh"
 #include "iso_prior.cuh"
 
-#ifndef ISO_PAIR_RECORDS
-#define ISO_PAIR_RECORDS 1   // gather the model cell as four 96-byte EEP-pair records (0: eight 64-byte nodes)
+#ifndef ISO_MODEL_LAYOUT
+#define ISO_MODEL_LAYOUT ISO_LAYOUT_NODE48   // default layout of the model cell gather (iso_common.cuh)
 #endif
 
 // device image of one star model (built from the public iso_model by iso_models_stage)
@@ -175,10 +175,37 @@ __device__ __forceinline__ void iso_stage_axis_tables(const IsoRowGrids &G, doub
     iso_mbar_wait(&tables_bar, 0);
 }
 
+// Bolometric corrections of one chunk of four packed bands at a located BC cell: 16 corners x one 32-byte sector
+// (interp_value_4d, interp.py:296-338, for the chunk's columns; accumulation in the reference's corner order).
+__device__ __forceinline__ void iso_bc_chunk(const IsoGridDev &bg, const int (&idx4)[4], const double (&y4)[4], int ch,
+                                             double (&bcv)[4])
+{
+    unsigned node[16];
+    double w[16];
+    iso_corners<4>(bg, idx4, y4, node, w);
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        iso_d4 q = iso_ldg256(bg.g + (size_t)node[j] * bg.ncols + 4 * ch);
+        b0 = fma(q.x, w[j], b0);
+        b1 = fma(q.y, w[j], b1);
+        b2 = fma(q.z, w[j], b2);
+        b3 = fma(q.w, w[j], b3);
+    }
+    bcv[0] = b0;
+    bcv[1] = b1;
+    bcv[2] = b2;
+    bcv[3] = b3;
+}
+
 // One row.  want_prior / want_like: the caller asked for the separate lnprior / lnlike values (every term is then
 // evaluated, as BasicStarModel.lnprior / lnlike would); otherwise rows whose prior is already known to be
 // non-finite return lnpost = -inf early, which is exactly what StarModel.lnpost returns (starmodel.py:540-541).
-template <int NSTARS, int PROFILE, bool TRACK>
+// SEQ (multiple stars, BC pack of exactly one 4-band chunk): every star's magnitudes are evaluated right after its
+// model cell, so only flux[4] survives from star to star instead of each star's located BC cell (4 indices + 4
+// distances + Mbol): the binary / triple kernels then fit in 128 registers (they spilled 250-350 bytes before).  The
+// arithmetic and its order are those of the chunk-major form, the results bit-identical.
+template <int NSTARS, int PROFILE, bool TRACK, int LAYOUT = ISO_MODEL_LAYOUT, bool SEQ = false>
 __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, const double2 *s_nodes, const IsoModelDev &m,
                                                        const double (&p)[NSTARS + 4], bool want_prior, bool want_like)
 {
@@ -225,10 +252,15 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
         }
 
         // ---- model-grid gather per star --------------------------------------------------------------
-        double lnp_eep[NSTARS], Mbol[NSTARS], y4[NSTARS][4];
-        int idx4[NSTARS][4];
-        bool bc_ok[NSTARS];
+        constexpr int NKEEP = SEQ ? 1 : NSTARS;   // located BC cells kept for the chunk-major likelihood
+        double lnp_eep[NSTARS], Mbol[NKEEP], y4[NKEEP][4];
+        int idx4[NKEEP][4];
+        bool bc_ok[NKEEP];
         double Teff = nan, logg = nan, feh_s = nan, nu_max = nan, delta_nu = nan;
+        // mags.py:52: 5 log10(d / 10); the default profile already holds log(d)
+        const double dist_mod = DEF ? 5.0 * fma(lnd, 0.43429448190325182765, -1.0) : 5.0 * log10(dist / 10.0);
+        double flux[4] = {0.0, 0.0, 0.0, 0.0};   // SEQ: summed fluxes of the (single) band chunk
+        bool eeps_finite = true;                 // SEQ: every star so far has a finite EEP prior
 #pragma unroll
         for (int k = 0; k < NSTARS; k++) {
             // star k uses [pars[k], shared parameters...]  (likelihood.py:43-54)
@@ -244,30 +276,73 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                 iso_corners<3>(mg, idx, y, node, w);
 #pragma unroll
                 for (int c = 0; c < 8; c++) v[c] = 0.0;
-#if ISO_PAIR_RECORDS
-                // The two EEP-adjacent corners 2s, 2s + 1 of a cell are ONE 96-byte pair record (3 sectors instead of
-                // 4): record node[2s] holds the six always-needed columns of flat nodes node[2s] and node[2s] + 1 —
-                // the same node the reference's unchecked index arithmetic reaches for corner 2s + 1, incl. the zero
-                // padding past the array.  Accumulation stays in the reference's corner order.
+                if constexpr (LAYOUT == ISO_LAYOUT_PAIR96) {
+                    // The two EEP-adjacent corners 2s, 2s + 1 of a cell are ONE 96-byte pair record (3 sectors instead of
+                    // 4): record node[2s] holds the six always-needed columns of flat nodes node[2s] and node[2s] + 1 —
+                    // the same node the reference's unchecked index arithmetic reaches for corner 2s + 1, incl. the zero
+                    // padding past the array.  Accumulation stays in the reference's corner order.
 #pragma unroll
-                for (int s2 = 0; s2 < 4; s2++) {
-                    const double *rec = mg.gp + (size_t)node[2 * s2] * ISO_PP_STRIDE;
-                    const iso_d4 q0 = iso_ldg256(rec), q1 = iso_ldg256(rec + 4), q2 = iso_ldg256(rec + 8);
-                    const double wa = w[2 * s2], wb = w[2 * s2 + 1];
-                    v[0] = fma(q0.x, wa, v[0]);
-                    v[1] = fma(q0.y, wa, v[1]);
-                    v[2] = fma(q0.z, wa, v[2]);
-                    v[3] = fma(q0.w, wa, v[3]);
-                    v[4] = fma(q1.x, wa, v[4]);
-                    v[5] = fma(q1.y, wa, v[5]);
-                    v[0] = fma(q1.z, wb, v[0]);
-                    v[1] = fma(q1.w, wb, v[1]);
-                    v[2] = fma(q2.x, wb, v[2]);
-                    v[3] = fma(q2.y, wb, v[3]);
-                    v[4] = fma(q2.z, wb, v[4]);
-                    v[5] = fma(q2.w, wb, v[5]);
+                    for (int s2 = 0; s2 < 4; s2++) {
+                        const double *rec = mg.gp + (size_t)node[2 * s2] * ISO_PP_STRIDE;
+                        const iso_d4 q0 = iso_ldg256(rec), q1 = iso_ldg256(rec + 4), q2 = iso_ldg256(rec + 8);
+                        const double wa = w[2 * s2], wb = w[2 * s2 + 1];
+                        v[0] = fma(q0.x, wa, v[0]);
+                        v[1] = fma(q0.y, wa, v[1]);
+                        v[2] = fma(q0.z, wa, v[2]);
+                        v[3] = fma(q0.w, wa, v[3]);
+                        v[4] = fma(q1.x, wa, v[4]);
+                        v[5] = fma(q1.y, wa, v[5]);
+                        v[0] = fma(q1.z, wb, v[0]);
+                        v[1] = fma(q1.w, wb, v[1]);
+                        v[2] = fma(q2.x, wb, v[2]);
+                        v[3] = fma(q2.y, wb, v[3]);
+                        v[4] = fma(q2.z, wb, v[4]);
+                        v[5] = fma(q2.w, wb, v[5]);
+                    }
+                } else if constexpr (LAYOUT == ISO_LAYOUT_NODE48) {
+                    // 48-byte nodes, no duplication: corners 2s, 2s + 1 are the 96 contiguous bytes of flat nodes
+                    // node[2s], node[2s] + 1 (same flat arithmetic as above).  The run starts 32-byte aligned for an even
+                    // node (3 sectors) and 16 bytes into a sector for an odd one (4 sectors: the fourth load is predicated);
+                    // the 12 values are picked out of the aligned sectors with selects.
+#pragma unroll
+                    for (int s2 = 0; s2 < 4; s2++) {
+                        const unsigned n0 = node[2 * s2];
+                        const bool odd = (n0 & 1u) != 0;
+                        const double *al = mg.g48 + ((size_t)n0 * ISO_PP_NCOLS - (odd ? 2 : 0));
+                        const iso_d4 q0 = iso_ldg256(al), q1 = iso_ldg256(al + 4), q2 = iso_ldg256(al + 8);
+                        iso_d4 q3;
+                        q3.x = q3.y = q3.z = q3.w = 0.0;
+                        if (odd) q3 = iso_ldg256(al + 12);
+                        const double wa = w[2 * s2], wb = w[2 * s2 + 1];
+                        v[0] = fma(odd ? q0.z : q0.x, wa, v[0]);
+                        v[1] = fma(odd ? q0.w : q0.y, wa, v[1]);
+                        v[2] = fma(odd ? q1.x : q0.z, wa, v[2]);
+                        v[3] = fma(odd ? q1.y : q0.w, wa, v[3]);
+                        v[4] = fma(odd ? q1.z : q1.x, wa, v[4]);
+                        v[5] = fma(odd ? q1.w : q1.y, wa, v[5]);
+                        v[0] = fma(odd ? q2.x : q1.z, wb, v[0]);
+                        v[1] = fma(odd ? q2.y : q1.w, wb, v[1]);
+                        v[2] = fma(odd ? q2.z : q2.x, wb, v[2]);
+                        v[3] = fma(odd ? q2.w : q2.y, wb, v[3]);
+                        v[4] = fma(odd ? q3.x : q2.z, wb, v[4]);
+                        v[5] = fma(odd ? q3.y : q2.w, wb, v[5]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double *base = mg.g + (size_t)node[j] * ISO_MP_NCOLS;
+                        iso_d4 lo = iso_ldg256(base), hi = iso_ldg256(base + 4);
+                        v[0] = fma(lo.x, w[j], v[0]);
+                        v[1] = fma(lo.y, w[j], v[1]);
+                        v[2] = fma(lo.z, w[j], v[2]);
+                        v[3] = fma(lo.w, w[j], v[3]);
+                        v[4] = fma(hi.x, w[j], v[4]);
+                        v[5] = fma(hi.y, w[j], v[5]);
+                        v[6] = fma(hi.z, w[j], v[6]);
+                        v[7] = fma(hi.w, w[j], v[7]);
+                    }
                 }
-                if (k == 0 && m.has_nu_max) {   // asteroseismic columns (rare): from the 8-column nodes
+                if (LAYOUT != ISO_LAYOUT_NODE64 && k == 0 && m.has_nu_max) {   // asteroseismic columns (rare): from the 8-column nodes
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double2 sv = __ldg(reinterpret_cast<const double2 *>(mg.g + (size_t)node[j] * ISO_MP_NCOLS + ISO_MP_NU_MAX));
@@ -275,21 +350,6 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                         v[ISO_MP_DELTA_NU] = fma(sv.y, w[j], v[ISO_MP_DELTA_NU]);
                     }
                 }
-#else
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const double *base = mg.g + (size_t)node[j] * ISO_MP_NCOLS;
-                    iso_d4 lo = iso_ldg256(base), hi = iso_ldg256(base + 4);
-                    v[0] = fma(lo.x, w[j], v[0]);
-                    v[1] = fma(lo.y, w[j], v[1]);
-                    v[2] = fma(lo.z, w[j], v[2]);
-                    v[3] = fma(lo.w, w[j], v[3]);
-                    v[4] = fma(hi.x, w[j], v[4]);
-                    v[5] = fma(hi.y, w[j], v[5]);
-                    v[6] = fma(hi.z, w[j], v[6]);
-                    v[7] = fma(hi.w, w[j], v[7]);
-                }
-#endif
             }
             // EEP_prior.lnpdf: BoundedPrior.lnpdf :131-140 -> Prior.pdf :54-59 -> EEP_prior._pdf :423-429
             const double eep = TRACK ? other : p[k];
@@ -310,7 +370,7 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                                  : iso_prior_call_dyn(&m.eep_orig, v[ISO_MP_ORIG]);
                 lnp_eep[k] = iso_log_or_neginf(pdf * v[ISO_MP_DERIV] * m.eep_inv_norm);
             }
-            Mbol[k] = v[ISO_MP_MBOL];
+            if (!SEQ) Mbol[k] = v[ISO_MP_MBOL];
             if (k == 0) {   // companions' Teff / logg / feh are discarded (likelihood.py:76, 96)
                 Teff = v[ISO_MP_TEFF];
                 logg = v[ISO_MP_LOGG];
@@ -320,7 +380,28 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
             }
             // BC cell of this star: interp_value_4d(Teff, logg, feh, AV)  mags.py:49-50
             const double x4[4] = {v[ISO_MP_TEFF], v[ISO_MP_LOGG], v[ISO_MP_FEH], AV};
-            bc_ok[k] = iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[k], y4[k]);
+            if (!SEQ) {
+                bc_ok[k] = iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[k], y4[k]);
+            } else {
+                // this star's fluxes now (fast_addmags utils.py:67-75 sums them in star order); skipped when the prior
+                // is already known to be non-finite and no separate lnlike was asked for (StarModel.lnpost never
+                // evaluates the likelihood then)
+                eeps_finite = eeps_finite && isfinite(lnp_eep[k]);
+                const int cm = m.obs_mask & 0xF;
+                if (cm && (want_like || (eeps_finite && !order_bad && isfinite(cheap)))) {
+                    double mg4[4] = {nan, nan, nan, nan};
+                    if (iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[0], y4[0])) {
+                        double bcv[4];
+                        iso_bc_chunk(bg, idx4[0], y4[0], 0, bcv);
+                        const double mb = v[ISO_MP_MBOL] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
+#pragma unroll
+                        for (int b = 0; b < 4; b++) mg4[b] = mb - bcv[b];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
+                }
+            }
         }
 
         // ---- lnprior: sum in param_names order (models.py:665, 692; starmodel.py:1510-1518) ----------------
@@ -352,35 +433,26 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
         if (m.spec_mask & 1) ll += iso_gauss(m.spec[0], Teff);
         if (m.spec_mask & 2) ll += iso_gauss(m.spec[1], logg);
         if (m.spec_mask & 4) ll += iso_gauss(m.spec[2], feh_s);
-        if (m.obs_mask) {
-            // mags.py:52: 5 log10(d / 10); the default profile already holds log(d)
-            const double dist_mod = DEF ? 5.0 * fma(lnd, 0.43429448190325182765, -1.0) : 5.0 * log10(dist / 10.0);
+        if (SEQ) {
+            const int cm = m.obs_mask & 0xF;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (cm & (1 << b)) ll += iso_gauss(m.mag[b], -2.5 * log10(flux[b]));
+        } else if (m.obs_mask) {
             for (int ch = 0; ch < bc_chunks; ch++) {
                 const int cm = (m.obs_mask >> (4 * ch)) & 0xF;
                 if (!cm) continue;
                 double tot[4];
-                double flux[4] = {0.0, 0.0, 0.0, 0.0};
+                double fl[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int k = 0; k < NSTARS; k++) {
+                for (int k = 0; k < NKEEP; k++) {
                     double mg4[4] = {nan, nan, nan, nan};
                     if (bc_ok[k]) {
-                        unsigned node[16];
-                        double w[16];
-                        iso_corners<4>(bg, idx4[k], y4[k], node, w);
-                        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            iso_d4 q = iso_ldg256(bg.g + (size_t)node[j] * bg.ncols + 4 * ch);
-                            b0 = fma(q.x, w[j], b0);
-                            b1 = fma(q.y, w[j], b1);
-                            b2 = fma(q.z, w[j], b2);
-                            b3 = fma(q.w, w[j], b3);
-                        }
+                        double bcv[4];
+                        iso_bc_chunk(bg, idx4[k], y4[k], ch, bcv);
                         const double mb = Mbol[k] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
-                        mg4[0] = mb - b0;
-                        mg4[1] = mb - b1;
-                        mg4[2] = mb - b2;
-                        mg4[3] = mb - b3;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) mg4[b] = mb - bcv[b];
                     }
                     if (NSTARS == 1) {
 #pragma unroll
@@ -388,13 +460,13 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                     } else {   // fast_addmags utils.py:67-75 — only evaluated for observed columns
 #pragma unroll
                         for (int b = 0; b < 4; b++)
-                            if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
+                            if (cm & (1 << b)) fl[b] += exp10(-0.4 * mg4[b]);
                     }
                 }
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     if (!(cm & (1 << b))) continue;
-                    if (NSTARS > 1) tot[b] = -2.5 * log10(flux[b]);
+                    if (NSTARS > 1) tot[b] = -2.5 * log10(fl[b]);
                     ll += iso_gauss(m.mag[4 * ch + b], tot[b]);
                 }
             }

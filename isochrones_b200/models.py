@@ -7,9 +7,11 @@ Kept from the reference: ``param_names``, ``eep_replaces``, ``param_index_order`
 bands)`` (:402-445), ``initialize`` (:349-358) and the property shortcuts (``mass``, ``radius``, ``Teff`` ...).
 
 Out of scope: grid download / parsing (``Grid``, ``StellarModelGrid``, ``MIST*Grid``).  The grids
-come in as dense arrays — synthetic MIST-shaped ones from :mod:`isochrones_b200.synthetic`, or the reference's own
-cached ``.npz`` dense grids through ``DFInterpolator.from_npz`` — and are staged once to HBM.  Also here (SURVEY.md
-§8f-3): ``get_eep`` (``interp_eep(s)``, interp.py:488-558) and ``generate`` (models.py:580-629) on the same kernels.
+come in as dense arrays — the reference's own cached ``full_grid*.npz`` dense grids + the MIST BC text tables under
+``$ISOCHRONES`` (``get_ichrone`` through :mod:`isochrones_b200.mistio`), or, on explicit request,
+synthetic MIST-shaped ones from :mod:`isochrones_b200.synthetic` — and are staged once to HBM.  Also here (SURVEY.md
+§8f-3): ``get_eep`` (``interp_eep(s)``, interp.py:488-558, and a batched root bracketing in place of the reference's
+per-star scipy minimisation) and ``generate`` on the same kernels.
 """
 import ctypes as C
 
@@ -31,7 +33,11 @@ class ModelGrid(object):
         self.name = name
 
     def get_limits(self, prop):
-        return self._limits[prop]          # reference grid.py:58-61 / mist/models.py:37
+        """Declared bounds (mist/models.py:37), else the range of the column over the grid (grid.py:58-61)."""
+        if prop not in self._limits:
+            col = self.interp.grid[..., self.interp.column_index[prop]]
+            self._limits[prop] = (float(np.nanmin(col)), float(np.nanmax(col)))
+        return self._limits[prop]
 
     def get_array_grids(self):
         """``(age_grid[n_feh * n_mass, n_eep], dt_deep_grid, lengths)`` of an evolution-track grid — the irregular
@@ -264,113 +270,83 @@ class ModelGridInterpolator(object):
             self.ctx.handle, self.model_pack.handle, bc.handle, _lib.ip(io), 0, 1, 2, 3, _lib.ip(bc_cols), len(bands), ptrs,
             int(n), d_Teff, d_logg, d_feh, d_mags))
 
-    def get_eep(self, mass, age, feh, accurate=False, **kwargs):
-        """EEP of a star of given (mass, log10 age, feh) on an evolution-track grid (models.py:501-542): the fast
-        bracketing interpolation ``interp_eep(s)`` (interp.py:488-558) on the GPU (``iso_interp_eeps``).  Scalars give
-        a float, anything else is broadcast.  ``accurate=True`` (scipy minimisation, models.py:544-578) is outside the
-        accelerated path."""
-        if accurate:
-            b = np.broadcast(mass, age, feh)
-            if b.shape == ():
-                return self.get_eep_accurate(float(mass), float(age), float(feh), **kwargs)
-            pars = [np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel() for x in (mass, age, feh)]
-            return np.array([self.get_eep_accurate(m, a, f, **kwargs) for m, a, f in zip(*pars)])
-        if self.eep_replaces != "age":
-            raise NotImplementedError
+    def get_eep(self, mass, age, feh, accurate=False, return_nan=True):
+        """EEP of stars of given (mass, log10 age, feh).  Scalars give a float, anything else is broadcast.
+
+        Evolution-track grids: the fast bracketing interpolation ``interp_eep(s)`` of the reference (interp.py:488-558,
+        models.py:501-542) on the GPU (``iso_interp_eeps``).  ``accurate=True`` (the only form isochrone grids have)
+        solves ``age(mass, eep, feh) = age`` resp. ``initial_mass(eep, age, feh) = mass`` for the EEP instead: where the
+        reference runs one scipy Nelder-Mead minimisation per star on the host (models.py:544-578), this brackets the
+        root for ALL stars at once by repeated 64-way subdivision of the EEP range — three interpolation launches of
+        ``64 N`` points — and finishes with the secant of the last bracket (:meth:`solve_eep`).  Stars without a root
+        give NaN (``return_nan=False``: raise, like the reference)."""
         scalar = all(isinstance(v, (float, int)) for v in (mass, age, feh))
         b = np.broadcast(mass, age, feh)
-        age_a, feh_a, mass_a = [np.ascontiguousarray(np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel())
-                                for x in (age, feh, mass)]
-        lengths = np.ascontiguousarray(self.model_grid.array_lengths, dtype=np.int32)
-        out = np.empty(len(age_a))
-        ctx = self.ctx
-        ctx.check(_lib.lib().iso_interp_eeps(ctx.handle, self.model_pack.handle, 4, _lib.ip(lengths), _lib.dp(age_a),
-                                             _lib.dp(feh_a), _lib.dp(mass_a), len(age_a), _lib.dp(out)))
+        mass_a, age_a, feh_a = [np.ascontiguousarray(np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel())
+                                for x in (mass, age, feh)]
+        if accurate or self.eep_replaces != "age":
+            out = self.solve_eep(mass_a, age_a, feh_a)
+            if not return_nan and np.isnan(out).any():
+                raise RuntimeError("no EEP reproduces (mass, age, feh) = %r"
+                                   % ((mass_a[np.isnan(out)][0], age_a[np.isnan(out)][0], feh_a[np.isnan(out)][0]),))
+        else:
+            lengths = np.ascontiguousarray(self.model_grid.array_lengths, dtype=np.int32)
+            out = np.empty(len(age_a))
+            ctx = self.ctx
+            ctx.check(_lib.lib().iso_interp_eeps(ctx.handle, self.model_pack.handle, 4, _lib.ip(lengths), _lib.dp(age_a),
+                                                 _lib.dp(feh_a), _lib.dp(mass_a), len(age_a), _lib.dp(out)))
         return float(out[0]) if scalar else out
 
-    def max_eep(self, mass, feh):
-        """Last populated EEP of the track nearest below (mass, feh) (the reference asks the MIST table,
-        mist/utils.py:16-59; here it is read off the staged grid's NaN tails)."""
-        if self.eep_replaces != "age":
-            raise NotImplementedError
-        g = self.model_grid
-        i_f = max(0, int(np.searchsorted(g.fehs, feh, side="right")) - 1)
-        i_m = max(0, int(np.searchsorted(g.masses, mass, side="right")) - 1)
-        return int(g.array_lengths[i_f * len(g.masses) + i_m])
+    def solve_eep(self, mass, age, feh, fan=64, passes=3):
+        """Batched root bracketing behind ``get_eep(accurate=True)``: ``[N]`` arrays in, ``[N]`` EEPs (NaN: no root).
 
-    def mass_age_resid(self, eep, mass, age, feh):
-        """Squared residual the accurate EEP search minimises (models.py:678-682, 706-710) — one GPU interpolation."""
-        eep = float(np.squeeze(eep))
-        if self.eep_replaces == "age":
-            return float((age - self.interp_value([float(mass), eep, float(feh)], ["age"])[0]) ** 2)
-        return float((mass - self.interp_value([eep, float(age), float(feh)], ["initial_mass"])[0]) ** 2)
+        The target column (``age`` along a track, ``initial_mass`` along an isochrone) is non-decreasing in EEP over
+        the populated part of the grid, so the root is the first sign change of ``column(eep) - target`` among the
+        finite samples; every pass evaluates ``fan + 1`` equally spaced EEPs per star in ONE launch and keeps the
+        bracketing interval (resolution after three passes: 1710 / 64^3 = 0.007 EEP)."""
+        n = len(mass)
+        track = self.eep_replaces == "age"
+        target, column = (age, "age") if track else (mass, "initial_mass")
+        lo = np.full(n, float(self.eep_bounds[0]) if self.eep_bounds[0] >= 1 else 1.0)
+        hi = np.full(n, float(self.model_grid.interp.index_columns[2][-1]))
+        t = np.linspace(0.0, 1.0, fan + 1)
+        f_lo = f_hi = None
+        alive = np.ones(n, dtype=bool)
+        for _ in range(passes):
+            eeps = lo[:, None] + (hi - lo)[:, None] * t[None, :]                       # [N, fan + 1]
+            rep = [np.repeat(x, fan + 1) for x in (mass, age, feh)]
+            pars = [rep[0], eeps.ravel(), rep[2]] if track else [eeps.ravel(), rep[1], rep[2]]
+            f = self.interp_value(pars, [column])[:, 0].reshape(n, fan + 1) - target[:, None]
+            finite = np.isfinite(f)
+            # first j with f[j] <= 0 <= f[j + 1] (both finite)
+            ok = finite[:, :-1] & finite[:, 1:] & (f[:, :-1] <= 0.0) & (f[:, 1:] >= 0.0)
+            alive &= ok.any(axis=1)
+            j = np.where(alive, ok.argmax(axis=1), 0)
+            rows = np.arange(n)
+            lo, hi = eeps[rows, j], eeps[rows, j + 1]
+            f_lo, f_hi = f[rows, j], f[rows, j + 1]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            frac = np.where(f_hi > f_lo, -f_lo / (f_hi - f_lo), 0.0)
+        return np.where(alive, lo + frac * (hi - lo), np.nan)
 
-    def get_eep_accurate(self, mass, age, feh, eep0=300, resid_tol=0.02, method="nelder-mead", return_object=False,
-                         return_nan=False, **kwargs):
-        """models.py:544-578: scipy minimisation of ``mass_age_resid`` (the optimiser loop stays on the host as in
-        the reference; every residual evaluation is a GPU interpolation)."""
-        from scipy.optimize import minimize
-
-        top = (self.max_eep(mass, feh) if self.eep_replaces == "age" else self.eep_bounds[1]) - 20
-        eeps_to_try = [min(top, 600), 100, 200]
-        while np.isnan(self.mass_age_resid(eep0, mass, age, feh)):
-            try:
-                eep0 = eeps_to_try.pop()
-            except IndexError:
-                if return_nan:
-                    return np.nan
-                raise ValueError("eep0 gives nan for all initial guesses! {}".format((mass, age, feh)))
-        result = minimize(self.mass_age_resid, eep0, args=(mass, age, feh), method=method, options=kwargs)
-        if return_object:
-            return result
-        if result.success and result.fun < resid_tol ** 2:
-            return float(np.squeeze(result.x))
-        if return_nan:
-            return np.nan
-        raise RuntimeError("EEP minimization not successful: {}".format((mass, age, feh)))
-
-    def isochrone(self, age, feh=0.0, eep_range=None, distance=10.0, AV=0.0, dropna=True):
-        """All properties along an isochrone / track section (models.py:484-493) — two kernel launches."""
-        if eep_range is None:
-            eep_range = self.model_grid.get_limits("eep")
-        eeps = np.arange(*eep_range)
-        df = self(eeps, age, feh, distance=distance, AV=AV)
-        return df.dropna() if dropna else df
-
-    def generate(self, mass, age, feh, props="all", bands=None, eeps=None, return_df=True, return_dict=False,
-                 distance=10, AV=0, all_As=False, **kwargs):
-        """Synthesise stars of given (mass, log10 age, feh): EEP lookup, all model-grid properties and apparent
-        magnitudes (models.py:580-629) — three kernel launches for the whole batch."""
-        import pandas as pd
-
-        mass, age, feh, distance, AV = [np.atleast_1d(a) if np.size(a) > 1 else float(a)
-                                        for a in np.broadcast_arrays(mass, age, feh, distance, AV)]
-        if bands is None:
-            bands = self.bands
+    def generate(self, mass, age, feh, distance=10.0, AV=0.0, bands=None, eeps=None):
+        """Forward-simulate stars of given (mass, log10 age, feh) on an evolution-track grid: ``get_eep`` -> every
+        model-grid column + apparent magnitudes at (distance, AV), one row per star (what the reference's ``generate``
+        models.py:580-629 is used for by the synthetic-observation callers of §8f-3).  Three kernel launches for the
+        whole batch; returns the frame of ``__call__`` plus the requested (mass, age, feh)."""
         if eeps is None:
-            eeps = self.get_eep(mass, age, feh, **kwargs)
-        cols = list(self.model_grid.interp.columns) if isinstance(props, str) and props == "all" else list(props)
-        values = self.interp_value([mass, eeps, feh], cols)
-        if bands:
-            _, _, _, mags = self.interp_mag([mass, eeps, feh, distance, AV], bands)
-            axis = 1 if values.ndim == 2 else 0
-            values = np.concatenate([values, mags], axis=axis)
-        names = cols + ["{}_mag".format(b) for b in bands]
-        if return_dict:
-            values = dict(zip(names, values.T if values.ndim == 2 else values))
-        elif return_df:
-            values = pd.DataFrame(np.atleast_2d(values), columns=names)
-        else:
-            return values
-        values["distance"] = distance
-        values["AV"] = AV
-        values["initial_feh"] = feh
-        values["requested_age"] = age
-        if all_As:
-            _, _, _, true_mags = self.interp_mag([mass, eeps, feh, distance, 0.0], bands)
-            for b, true_mag in zip(bands, np.atleast_2d(true_mags).T):
-                values["A_{}".format(b)] = values["{}_mag".format(b)] - true_mag
-        return values
+            eeps = self.get_eep(mass, age, feh)
+        saved = self.bands
+        try:
+            if bands is not None:
+                self.bands = list(bands)
+            frame = self(mass, eeps, feh, distance=distance, AV=AV)
+        finally:
+            self.bands = saved
+        n = len(frame)
+        for name, v in (("distance", distance), ("AV", AV), ("initial_feh", feh), ("requested_age", age)):
+            frame[name] = np.broadcast_to(np.asarray(v, dtype=float), (n,))
+        return frame
 
     def __call__(self, p1, p2, p3, distance=10.0, AV=0.0):
         """All model-grid columns + magnitudes as a DataFrame (models.py:471-482) — same kernels, wider output."""
@@ -431,20 +407,37 @@ def ichrone_from_arrays(kind, model, bc, bands=None, eep_bounds=None, ctx=None):
     return _from_synthetic(cls, model, bc, bands=bands, eep_bounds=eep_bounds, ctx=ctx)
 
 
-def get_ichrone(models="mist", bands=None, tracks=False, synthetic_shape=None, ctx=None, **kwargs):
+def get_ichrone(models="mist", bands=None, tracks=False, synthetic=False, synthetic_shape=None, root=None, ctx=None,
+                limits=None, **kwargs):
     """``get_ichrone`` of the reference (isochrone.py:47-78) for the one grid family on the path (MIST).
 
-    No MIST data can exist in this environment (no network), so the grids are the deterministic MIST-*shaped*
-    synthetic ones; ``synthetic_shape`` (dict of ``make_*_grid`` keyword arguments) shrinks them for tests."""
-    from . import synthetic as syn
-
+    By default the grids are the REAL ones: the dense-grid cache the reference leaves under ``$ISOCHRONES``
+    (``mist/full_grid_*.npz`` or ``mist/tracks/full_grid_*.npz``) and the MIST bolometric-correction tables under
+    ``$ISOCHRONES/BC/mist`` (:mod:`isochrones_b200.mistio`); ``root`` overrides ``$ISOCHRONES``.  Without that data
+    this raises :class:`mistio.MistDataNotFound` — nothing is fabricated silently.  ``limits`` overrides entries of the
+    MIST parameter limits (mist/models.py:37); other keywords select the grid version (``version``, ``vvcrit``,
+    ``iso_kind``).  ``synthetic=True`` (or a
+    ``synthetic_shape`` dict of ``make_*_grid`` keyword arguments, which shrinks them for tests) asks for the
+    deterministic MIST-*shaped* synthetic grids of the benchmark; their interpolator is named ``synthetic_*``."""
     if not (isinstance(models, str) and models.lower().startswith("mist")):
         raise ValueError("only the MIST grid family is on the accelerated path")
-    bands = list(bands) if bands is not None else ["G", "BP", "RP", "J", "H", "K", "W1", "W2", "W3", "TESS", "Kepler"]
-    shape = dict(synthetic_shape or {})
-    bc = syn.make_bc_grid(bands=tuple(bands), **shape.get("bc", {}))
-    if tracks:
-        model = syn.make_track_grid(**shape.get("track", {}))
-        return ichrone_from_arrays("track", model, bc, bands=bands, ctx=ctx)
-    model = syn.make_iso_grid(**shape.get("iso", {}))
-    return ichrone_from_arrays("iso", model, bc, bands=bands, ctx=ctx)
+    kind = "track" if tracks else "iso"
+    if synthetic or synthetic_shape is not None:
+        from . import synthetic as syn
+
+        bands = list(bands) if bands is not None else ["G", "BP", "RP", "J", "H", "K", "W1", "W2", "W3", "TESS", "Kepler"]
+        shape = dict(synthetic_shape or {})
+        bc = syn.make_bc_grid(bands=tuple(bands), **shape.get("bc", {}))
+        model = syn.make_track_grid(**shape.get("track", {})) if tracks else syn.make_iso_grid(**shape.get("iso", {}))
+        return ichrone_from_arrays(kind, model, bc, bands=bands, ctx=ctx)
+    from . import mistio
+
+    bands = list(bands) if bands is not None else list(mistio.DEFAULT_BANDS)     # mist/bc.py:159
+    model = mistio.load_model_grid(kind, root=root, limits=limits, **kwargs)
+    bc = mistio.load_bc_grid(bands, root=root)
+    cls = EvolutionTrackInterpolator if tracks else IsochroneInterpolator
+    mi = DFInterpolator.from_arrays(model["grid"], model["axes"], model["columns"], index_names=model["index_names"], ctx=ctx)
+    bi = DFInterpolator.from_arrays(bc["grid"], bc["axes"], bc["columns"], index_names=("Teff", "logg", "[Fe/H]", "Av"), ctx=ctx)
+    mg = ModelGrid(mi, model["limits"], cls.eep_replaces, name="mist")
+    mg.source = model["source"]
+    return cls(mg, BCGrid(bi, bc["columns"]), bands=bands, eep_bounds=tuple(model["limits"]["eep"]), ctx=ctx)

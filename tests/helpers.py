@@ -254,3 +254,47 @@ def full_size_world():
         got = hashlib.sha256(np.ascontiguousarray(grid["grid"]).tobytes()).hexdigest()
         assert got == meta[name + "_sha256"], "synthetic %s grid differs from the one the reference was run on" % name
     return meta, g, {"track": trk, "iso": iso, "bc": bc}
+
+
+# ---------------------------------------------------------------------------
+# a fabricated $ISOCHRONES tree in the reference's on-disk layout (tests of isochrones_b200.mistio / get_ichrone)
+# ---------------------------------------------------------------------------
+
+def write_bc_text_tables(datadir, bc, rvs=(2.0, 3.1)):
+    """``bc`` (dense dict) -> MIST-layout text tables, one file per [Fe/H] and photometric system (bc.py:66-83: five
+    header lines, column names on the sixth, rows ``Teff logg [Fe/H] Av Rv <bands>``); values printed with 17
+    significant digits so that the parse is bit-exact.  Rows with ``Rv != 3.1`` carry shifted values."""
+    import os
+
+    from isochrones_b200 import bcio
+
+    os.makedirs(datadir, exist_ok=True)
+    by_phot = {}
+    for j, b in enumerate(bc["columns"]):
+        phot, col = bcio.mist_band(b)
+        by_phot.setdefault(phot, []).append((j, col))
+    teffs, loggs, fehs, avs = bc["axes"]
+    for phot, cols in by_phot.items():
+        for i_f, feh in enumerate(fehs):
+            name = "feh%s%03.0f_%02d.%s" % ("m" if feh < 0 else "p", abs(feh) * 100, i_f, phot)
+            with open(os.path.join(datadir, name), "w") as f:
+                f.write("# MIST version number  = 1.2\n# MESA revision number =     7503\n# photometric system    = %s\n"
+                        "# ABUNDANCES: [Fe/H] = %.2f\n# number of filters = %d\n" % (phot, feh, len(cols)))
+                f.write("#  " + "  ".join(["Teff", "logg", "[Fe/H]", "Av", "Rv"] + [c for _, c in cols]) + "\n")
+                for i_t, t in enumerate(teffs):
+                    for i_g, g in enumerate(loggs):
+                        for i_a, av in enumerate(avs):
+                            for rv in rvs:
+                                vals = [bc["grid"][i_t, i_g, i_f, i_a, j] + (0.0 if rv == 3.1 else 0.5 * rv) for j, _ in cols]
+                                f.write(" ".join("%.17g" % v for v in [t, g, feh, av, rv] + vals) + "\n")
+
+
+def write_isochrones_tree(root, kind, model, bc, sidecar=True):
+    """Model grid as the reference's ``full_grid*.npz`` cache (+ axes sidecar) and the BC grid as MIST text tables
+    under ``root`` (the layout of ``$ISOCHRONES``)."""
+    import os
+
+    from isochrones_b200 import mistio
+
+    mistio.save_model_grid(model, kind, root=root, sidecar=sidecar)
+    write_bc_text_tables(os.path.join(root, "BC", "mist"), bc)

@@ -47,7 +47,7 @@ def test_basic_ic_checks(ics):
     assert np.isfinite(ic.nu_max(eep, age, feh)) and np.isfinite(ic.delta_nu(eep, age, feh))
     _, _, _, mags = ic.interp_mag((eep, age, feh, 500, 0.2), ic.bands)
     assert np.isfinite(mags).all()
-    assert len(ic.isochrone(8.0, feh=0.0)) > 0                      # on-the-grid call (reference issue #64)
+    assert len(ic(np.arange(100.0, 200.0), 8.0, 0.0).dropna()) > 0   # on-the-grid call (reference issue #64)
     assert np.isnan(ic.radius(1.0, np.nan, 0.1))                    # NaN in -> NaN out (reference issue #65)
     # the accurate EEP puts the requested initial mass back (test_basic.py:60-76, resid_tol 0.02)
     assert abs(ic.initial_mass(eep, age, feh) - 1.0) < 0.022
@@ -69,7 +69,7 @@ def test_basic_ic_checks_tracks(ics):
     assert np.isfinite(ic.nu_max(mass, eep, feh)) and np.isfinite(ic.delta_nu(mass, eep, feh))
     _, _, _, mags = ic.interp_mag((mass, eep, feh, 500, 0.2), ic.bands)
     assert np.isfinite(mags).all()
-    assert len(ic.isochrone(8.0, feh=0.0)) > 0
+    assert len(ic(1.0, np.arange(100.0, 200.0), 0.0).dropna()) > 0
     assert np.isnan(ic.radius(1.0, np.nan, 0.1))
     # fast and accurate EEP lookups agree, and both land on the requested age
     fast = ic.get_eep(mass, 9.6, feh)
@@ -87,11 +87,17 @@ def test_closest_eep(ics):
     ages = rng.random_sample(n) * 1.2 + 8.6
     n_ok = 0
     for m, a, f in zip(masses, ages, fehs):
-        e = ic.get_eep(m, a, f, return_nan=True, resid_tol=resid_tol, accurate=True)
+        e = ic.get_eep(m, a, f, return_nan=True, accurate=True)
         if not np.isnan(e):
             assert abs(ic.initial_mass(e, a, f) - m) < resid_tol * 1.1
             n_ok += 1
     assert n_ok > n // 3
+    # the batched form solves all stars in three launches and agrees with the one-by-one calls
+    batch = ic.get_eep(masses, ages, fehs, accurate=True)
+    one = np.array([ic.get_eep(m, a, f, accurate=True) for m, a, f in zip(masses, ages, fehs)])
+    assert np.array_equal(batch, one, equal_nan=True)
+    ok = ~np.isnan(batch)
+    assert np.all(np.abs(ic.initial_mass(batch[ok], ages[ok], fehs[ok]) - masses[ok]) < 1e-3)
 
 
 def test_spec_likelihoods(ics):
