@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISO_ABI_VERSION 2
+#define ISO_ABI_VERSION 3
 
 #define ISO_OK 0
 #define ISO_E_INVALID (-1) /* bad argument */
@@ -36,6 +36,7 @@ extern "C" {
 #define ISO_E_NOMEM (-3)
 #define ISO_E_NCCL (-4)
 #define ISO_E_UNSUPPORTED (-5)
+#define ISO_E_TIMEOUT (-6) /* a peer rank did not publish an exchange step in time (iso_peer_*) */
 
 #define ISO_MAX_BANDS 16 /* photometric bands per star model */
 #define ISO_MAX_COMP 3   /* components of a BrokenPrior */
@@ -222,15 +223,34 @@ int iso_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *b
 int iso_lnpost_batch_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack,
                             const iso_models *models, const int32_t *d_model_of_row, const double *d_pars,
                             int64_t N, double *d_lnpost, double *d_lnprior, double *d_lnlike);
-/* BasicStarModel.mnest_prior (starmodel.py:1637-1640): cube[N, ndim] in place, u -> (hi - lo) u + lo. */
+/* BasicStarModel.mnest_prior (starmodel.py:1637-1640): cube[N, ndim] in place, u -> (hi - lo) u + lo (ndim <= 16;
+ * no device allocation per call: the bounds travel in the kernel parameter block). */
 int iso_mnest_prior(iso_ctx *ctx, const double *h_lo, const double *h_hi, int ndim, double *h_cube, int64_t N);
+/* mnest_prior + mnest_loglike (starmodel.py:1637-1645) of a batch of live points in ONE launch: h_cube[N, ndim] holds
+ * unit-cube points on entry and the mapped parameters on return (as mnest_prior leaves the cube), h_lnpost[N] their
+ * lnpost (= mnest_loglike); h_lnprior / h_lnlike may be NULL.  h_lo / h_hi: BasicStarModel.bounds per parameter. */
+int iso_mnest_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, double *h_cube, int64_t N, double *h_lnpost,
+                           double *h_lnprior, double *h_lnlike);
+/* N uniform draws from the box [lo, hi] evaluated where they are made: row i is the unit-cube point Philox4x32-10(seed,
+ * counter = row0 + i) mapped as above — nothing is shipped to the device per row (sample_from_prior /
+ * nested-sampling initialisation, starmodel.py:838-884).  h_pars[N, ndim] (may be NULL) receives the points. */
+int iso_lnpost_prior_draws(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, uint64_t seed, int64_t row0, int64_t N, double *h_pars,
+                           double *h_lnpost);
+/* Device-buffer form of the two calls above (asynchronous on the compute stream): rng = 0 reads unit-cube points from
+ * d_cube[N, ndim]; rng = 1 draws them (d_cube ignored).  d_pars (may be NULL, may alias d_cube) receives the mapped
+ * parameters. */
+int iso_lnpost_cube_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, const double *d_cube, int rng, uint64_t seed,
+                           int64_t row0, int64_t N, double *d_pars, double *d_lnpost);
 
 /* ------------------------------------------------------------------------------------------------
  * on-device ensemble sampler (the emcee stretch move the reference drives through
  * emcee.EnsembleSampler(nwalkers, npars, mod.lnpost), starmodel.py:966) — SURVEY.md §8f-1
  * ---------------------------------------------------------------------------------------------- */
 /* One persistent CTA per chain, one thread per walker of the active half (n_walkers even, <= 1024); the initial
- * lnpost of h_p0 is evaluated at creation.  `models` holds one model (every chain samples it) or n_chains models
+ * lnpost of h_p0 is evaluated at creation (a NaN there is an error, as in emcee; -inf walkers are legal).  `models` holds one model (every chain samples it) or n_chains models
  * (catalog mode: chain c samples star c).  Randomness is Philox4x32-10 keyed by `seed`. */
 int iso_sampler_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
                        int n_chains, int n_walkers, const double *h_p0 /* [n_chains, n_walkers, ndim] */,
@@ -242,6 +262,14 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
  * accepted proposals per chain (n_accepted[n_chains], may be NULL) and proposals made so far per chain. */
 int iso_sampler_state(iso_ctx *ctx, iso_sampler *s, double *h_pos, double *h_lnprob, int64_t *n_accepted,
                       int64_t *n_proposed);
+/* emcee's EnsembleSampler.reset(): zero the acceptance counters (and the proposal count they are divided by) and the
+ * running moments; the walkers stay where they are.  The burn-in / production split of the reference's
+ * fit_mcmc_old (starmodel.py:955-969). */
+int iso_sampler_reset(iso_ctx *ctx, iso_sampler *s);
+/* Running sums over every kept (thinned) ensemble since the last reset, per chain: [n_chains, 2 ndim + 1] =
+ * (sum x_d, sum x_d^2, number of samples).  h_moments (host copy; synchronises) and d_moments (the device array itself,
+ * e.g. as the send buffer of iso_allgather_f64 in a multi-GPU catalog fit) may each be NULL. */
+int iso_sampler_moments(iso_ctx *ctx, iso_sampler *s, double *h_moments, const double **d_moments);
 int iso_sampler_destroy(iso_ctx *ctx, iso_sampler *s);
 
 /* ------------------------------------------------------------------------------------------------
@@ -267,7 +295,35 @@ int iso_peer_connect(iso_ctx *ctx, iso_peer_group *group, const void *handles /*
 int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack,
                                 const iso_models *models, const int32_t *d_model_of_row, const double *d_pars,
                                 int64_t N, iso_peer_group *group, const double **d_gathered);
+/* The completion wait of a step is bounded (default 10 s of wall-clock time per step): when a rank does not publish a
+ * step in time the wait gives up, and the NEXT call on the group — or iso_peer_check, which first synchronises the
+ * stream — fails with ISO_E_TIMEOUT naming the missing rank.  The error is sticky: the group must be destroyed. */
+int iso_peer_set_timeout(iso_ctx *ctx, iso_peer_group *group, double seconds);
+int iso_peer_check(iso_ctx *ctx, iso_peer_group *group);
 int iso_peer_destroy(iso_ctx *ctx, iso_peer_group *group);
+
+/* ------------------------------------------------------------------------------------------------
+ * ONE ensemble sharded over the GPUs of a node: every rank holds the whole ensemble, moves its block
+ * of the active half per half-step and stores accepted walkers (position + lnpost) into every rank's copy through
+ * CUDA-IPC peer mappings inside the evaluation kernel; no collective launch.  Same stretch move and Philox stream as
+ * iso_sampler_*: the chain is independent of the number of ranks (bit for bit).  Setup as for iso_peer_*: create on
+ * every rank with the same h_p0 / seed, export 128 bytes, all-gather them, connect.  Every rank must call
+ * iso_ensemble_run with the same arguments; h_chain [n_steps / thin, n_walkers, ndim] and h_lnprob
+ * [n_steps / thin, n_walkers] (either may be NULL) receive the kept ensembles on every rank that asks.  A rank that
+ * stops participating turns into ISO_E_TIMEOUT on its peers (bounded wait, default 10 s per half-step).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct iso_ensemble iso_ensemble;
+int iso_ensemble_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                        int n_walkers, const double *h_p0 /* [n_walkers, ndim] */, uint64_t seed, double stretch_a,
+                        int rank, int nranks, iso_ensemble **out);
+int iso_ensemble_export(iso_ctx *ctx, iso_ensemble *e, void *handle128 /* 128 bytes */);
+int iso_ensemble_connect(iso_ctx *ctx, iso_ensemble *e, const void *handles /* [nranks][128], rank order */);
+int iso_ensemble_set_timeout(iso_ctx *ctx, iso_ensemble *e, double seconds);
+int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, double *h_chain, double *h_lnprob);
+/* current ensemble (either may be NULL), proposals accepted by THIS rank and proposals made per ensemble so far */
+int iso_ensemble_state(iso_ctx *ctx, iso_ensemble *e, double *h_pos, double *h_lnprob, int64_t *n_accepted_local,
+                       int64_t *n_proposed);
+int iso_ensemble_destroy(iso_ctx *ctx, iso_ensemble *e);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ entry point raises.  Build the library with ``python -c "import __graft_entry__ 
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -103,11 +104,27 @@ SIGNATURES = {
                                    c_double_p]),
     "iso_lnpost_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "iso_mnest_prior": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int64]),
+    "iso_mnest_lnpost_batch": (C.c_int, [_VP, _VP, _VP, _VP, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p,
+                                         c_double_p, c_double_p]),
+    "iso_lnpost_prior_draws": (C.c_int, [_VP, _VP, _VP, _VP, c_double_p, c_double_p, C.c_uint64, C.c_int64, C.c_int64,
+                                         c_double_p, c_double_p]),
+    "iso_lnpost_cube_device": (C.c_int, [_VP, _VP, _VP, _VP, c_double_p, c_double_p, _VP, C.c_int, C.c_uint64, C.c_int64,
+                                         C.c_int64, _VP, _VP]),
     "iso_sampler_create": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, c_double_p, C.c_uint64, C.c_double,
                                      C.POINTER(_VP)]),
     "iso_sampler_run": (C.c_int, [_VP, _VP, C.c_int, C.c_int, c_double_p, c_double_p]),
     "iso_sampler_state": (C.c_int, [_VP, _VP, c_double_p, c_double_p, c_int64_p, c_int64_p]),
+    "iso_sampler_reset": (C.c_int, [_VP, _VP]),
+    "iso_sampler_moments": (C.c_int, [_VP, _VP, c_double_p, C.POINTER(_VP)]),
     "iso_sampler_destroy": (C.c_int, [_VP, _VP]),
+    "iso_ensemble_create": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, c_double_p, C.c_uint64, C.c_double, C.c_int, C.c_int,
+                                      C.POINTER(_VP)]),
+    "iso_ensemble_export": (C.c_int, [_VP, _VP, _VP]),
+    "iso_ensemble_connect": (C.c_int, [_VP, _VP, _VP]),
+    "iso_ensemble_set_timeout": (C.c_int, [_VP, _VP, C.c_double]),
+    "iso_ensemble_run": (C.c_int, [_VP, _VP, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "iso_ensemble_state": (C.c_int, [_VP, _VP, c_double_p, c_double_p, c_int64_p, c_int64_p]),
+    "iso_ensemble_destroy": (C.c_int, [_VP, _VP]),
     "iso_nccl_unique_id": (C.c_int, [_VP]),
     "iso_nccl_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
     "iso_nccl_destroy": (C.c_int, [_VP]),
@@ -115,6 +132,8 @@ SIGNATURES = {
     "iso_peer_export": (C.c_int, [_VP, _VP, _VP]),
     "iso_peer_connect": (C.c_int, [_VP, _VP, _VP]),
     "iso_lnpost_allgather_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _VP, C.POINTER(_VP)]),
+    "iso_peer_set_timeout": (C.c_int, [_VP, _VP, C.c_double]),
+    "iso_peer_check": (C.c_int, [_VP, _VP]),
     "iso_peer_destroy": (C.c_int, [_VP, _VP]),
     "iso_allgather_f64": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
 }
@@ -204,7 +223,9 @@ class Context:
         self.check(lib().iso_host_alloc(self.handle, max(n, 1), C.byref(p)))
         buf = (C.c_char * max(n, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        _PINNED[id(buf)] = (self, p, buf)
+        # the page-locked block lives exactly as long as some numpy view of it: every view keeps `buf` alive through
+        # its base chain, and the finaliser of `buf` returns the block to the driver (iso_host_free)
+        weakref.finalize(buf, _free_pinned, self, p.value).atexit = False
         return arr
 
     def h2d(self, d_ptr, arr):
@@ -232,7 +253,13 @@ class Context:
             self.handle = _VP()
 
 
-_PINNED = {}      # keeps page-locked buffers alive for the life of the process
+def _free_pinned(ctx, address):
+    if ctx.handle:      # a destroyed context has released its allocations already
+        try:
+            lib().iso_host_free(ctx.handle, _VP(address))
+        except Exception:
+            pass
+
 _contexts = {}
 
 

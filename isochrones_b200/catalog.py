@@ -145,14 +145,5 @@ class StarCatalog(object):
         """All rows -> one ``CompiledModel`` with ``len(self)`` star models on the device (row i of the table = model i)."""
         arr, bands = self.build_structs(ic, N=N, maxAV=maxAV, max_distance=max_distance)
         n = len(arr)
-        compiled = CompiledModel.__new__(CompiledModel)
-        compiled.ic = ic
-        compiled.ctx = ic.ctx
-        compiled.n_models = n
-        compiled.n_stars = N
-        compiled.ndim = 4 + N
-        compiled.model_pack = ic.model_pack
-        compiled.bc_pack = ic.bc_pack(tuple(bands))
-        compiled.handle = C.c_void_p()
-        compiled.ctx.check(_lib.lib().iso_models_stage(compiled.ctx.handle, arr, n, C.byref(compiled.handle)))
+        compiled = CompiledModel.from_struct_array(ic, arr, n, N, tuple(bands))
         return compiled

@@ -7,192 +7,7 @@
 // EEP prior; nu_max, delta_nu) as 2 x LDG.256 per corner — and the BC cell as 16 corners x one 32-byte sector per
 // chunk of 4 packed bands.  The reference gathers the same model cell twice (once in EEP_prior, once in
 // interp_mag) and a third time for asteroseismology.
-#include "iso_lnpost_row.cuh"
-
-#ifndef ISO_LNPOST_THREADS
-#define ISO_LNPOST_THREADS 256
-#endif
-#ifndef ISO_LNPOST_MIN_BLOCKS
-#define ISO_LNPOST_MIN_BLOCKS 2
-#endif
-#ifndef ISO_LNPOST_MIN_BLOCKS_MULTI
-#define ISO_LNPOST_MIN_BLOCKS_MULTI 2   // binary / triple models: 128 registers + a small spill beats 1 CTA/SM at 255
-#endif
-#ifndef ISO_LNPOST_PREFETCH
-#define ISO_LNPOST_PREFETCH 1
-#endif
-#ifndef ISO_LNPOST_BLOCKS_PER_SM
-#define ISO_LNPOST_BLOCKS_PER_SM 2   // persistent grid: exactly the CTAs that are resident (2 per SM), rows grid-strided
-#endif
-
-struct IsoLnpostArgs {
-    const IsoModelDev *models;
-    const int *model_of_row;   // catalog mode only
-    const double *pars;        // [N, 4 + n_stars] row-major
-    double *lnpost, *lnprior, *lnlike;   // [N]; lnprior / lnlike may be NULL
-    long long N;
-    // fused all-gather (PEER kernels, iso_peer.cu): row i of this rank is stored at peer_out[r][peer_off + i] in the
-    // receive buffer of EVERY rank r (its own included) — plain stores over NVLink peer mappings
-    double *peer_out[ISO_MAX_PEERS];
-    long long peer_off;
-    int n_peers;
-    int peer_rank;
-    // completion signal of the fused all-gather: the last CTA to finish publishes `peer_step` in this rank's slot of
-    // every rank's flag array (release, system scope); peer_done counts finished CTAs and is reset by that CTA
-    unsigned long long *peer_flags[ISO_MAX_PEERS];
-    unsigned long long peer_step;
-    unsigned *peer_done;
-    unsigned long long *claim;   // dynamically scheduled kernels: [0] next unclaimed row beyond the first pass, [1] finished CTAs
-};
-
-// Everything the kernel reads besides the grids and the rows travels in the kernel parameter block (constant
-// bank): the grid descriptors, the buffer pointers and — outside catalog mode — the star model itself, so that
-// observation values and prior constants are constant-bank operands instead of memory loads.
-struct IsoLnpostParams {
-    IsoRowGrids G;
-    IsoLnpostArgs a;
-    IsoModelDev model;   // the single model (unused in catalog mode)
-};
-
-#ifndef ISO_LNPOST_DYN
-#define ISO_LNPOST_DYN 1
-#endif
-
-// Row scheduling of the persistent grid:
-//   DYN = 0 — static grid stride, the next row's parameters prefetched one iteration ahead;
-//   DYN = 1 — the first pass is the static one, after it every warp claims 32-row chunks from an atomic counter
-//             (a.claim[0]) so that the grid drains together whatever the rows cost (rows rejected by the grid-free
-//             priors cost a tenth of a full row; rows whose gathers miss the L2 several times a cached one).  Batches
-//             of at most one pass never touch the counters.  Round 2, B200, ms per 1e6 rows static -> dynamic:
-//             grid-wide 0.175 -> 0.165, prior-like 0.139 -> 0.134, binary 0.293 -> 0.274, posterior-like 0.121 = 0.121;
-//   DYN = 2 — the same with the claim and the row load issued one iteration ahead.
-// The last CTA to finish resets the counters (a.claim[1] counts finished CTAs), so a launch finds them zero.
-// SEQ: star-sequential evaluation of multi-star models whose BC pack is a single 4-band chunk (iso_lnpost_row.cuh).
-template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK, bool PEER = false, bool SEQ = false,
-          int LAYOUT = ISO_MODEL_LAYOUT, int DYN = ISO_LNPOST_DYN>
-__global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : ISO_LNPOST_MIN_BLOCKS_MULTI)
-iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
-{
-    constexpr int NDIMP = NSTARS + 4;
-    const IsoLnpostArgs &a = P.a;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
-    iso_stage_axis_tables(P.G, s_nodes);
-
-    const bool want_prior = a.lnprior != nullptr, want_like = a.lnlike != nullptr;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    auto eval_row = [&](long long row, const double (&p)[NDIMP]) {
-        const IsoModelDev &m = CATALOG ? a.models[a.model_of_row[row]] : P.model;
-        const IsoRowResult r = iso_lnpost_row<NSTARS, PROFILE, TRACK, LAYOUT, SEQ>(P.G, s_nodes, m, p, want_prior, want_like);
-        if (want_prior) a.lnprior[row] = r.lnprior;
-        if (want_like) a.lnlike[row] = r.lnlike;
-        if (PEER) {
-#pragma unroll
-            for (int q = 0; q < ISO_MAX_PEERS; q++)
-                if (q < a.n_peers) a.peer_out[q][a.peer_off + row] = r.lnpost;
-        } else {
-            a.lnpost[row] = r.lnpost;
-        }
-    };
-    if (DYN == 0) {
-#if ISO_LNPOST_PREFETCH
-        // software pipelining of the row stream: the next row's parameters are requested before this row is evaluated,
-        // so their HBM latency hides behind ~2000 instructions of work
-        double pn[NDIMP];
-        if (i < a.N) {
-#pragma unroll
-            for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[i * NDIMP + j];
-        }
-#endif
-        for (; i < a.N; i += stride) {
-            double p[NDIMP];
-#if ISO_LNPOST_PREFETCH
-#pragma unroll
-            for (int j = 0; j < NDIMP; j++) p[j] = pn[j];
-            if (i + stride < a.N) {
-#pragma unroll
-                for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[(i + stride) * NDIMP + j];
-            }
-#else
-#pragma unroll
-            for (int j = 0; j < NDIMP; j++) p[j] = a.pars[i * NDIMP + j];
-#endif
-            eval_row(i, p);
-        }
-    } else if (DYN == 1) {
-        const int lane = threadIdx.x & 31;
-        long long base = i - lane;   // warp-uniform: the static first pass
-        while (base < a.N) {
-            const long long row = base + lane;
-            if (row < a.N) {
-                double p[NDIMP];
-#pragma unroll
-                for (int j = 0; j < NDIMP; j++) p[j] = a.pars[row * NDIMP + j];
-                eval_row(row, p);
-            }
-            if (a.N <= stride) break;   // single pass: nothing to claim, the counters stay untouched
-            unsigned long long got = 0;
-            if (lane == 0) got = atomicAdd(a.claim, 32ULL);
-            base = stride + (long long)__shfl_sync(0xffffffffu, got, 0);
-        }
-    } else {
-        const int lane = threadIdx.x & 31;
-        long long base = i - lane;
-        double pn[NDIMP];
-        if (base + lane < a.N) {
-#pragma unroll
-            for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[(base + lane) * NDIMP + j];
-        }
-        unsigned long long got = 0;
-        if (lane == 0) got = atomicAdd(a.claim, 32ULL);
-        while (base < a.N) {
-            const long long row = base + lane;
-            double p[NDIMP];
-#pragma unroll
-            for (int j = 0; j < NDIMP; j++) p[j] = pn[j];
-            const long long nbase = stride + (long long)__shfl_sync(0xffffffffu, got, 0);
-            if (nbase + lane < a.N) {
-#pragma unroll
-                for (int j = 0; j < NDIMP; j++) pn[j] = a.pars[(nbase + lane) * NDIMP + j];
-            }
-            if (lane == 0 && nbase < a.N) got = atomicAdd(a.claim, 32ULL);
-            if (row < a.N) eval_row(row, p);
-            base = nbase;
-        }
-    }
-    if (DYN != 0 && !PEER && (DYN != 1 || a.N > stride)) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long ticket = atomicAdd(a.claim + 1, 1ULL);
-            if (ticket == gridDim.x - 1) {   // every CTA has made its last claim: leave the counters zero
-                a.claim[0] = 0;
-                a.claim[1] = 0;
-            }
-        }
-    }
-    if (PEER) {
-        // every thread's peer stores are ordered before its arrival; the last CTA then raises the flags
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(a.peer_done, 1u);
-            if (ticket == gridDim.x - 1) {
-                *a.peer_done = 0;
-                if (DYN != 0 && (DYN != 1 || a.N > stride)) {
-                    a.claim[0] = 0;
-                    a.claim[1] = 0;
-                }
-                __threadfence_system();
-#pragma unroll
-                for (int q = 0; q < ISO_MAX_PEERS; q++)
-                    if (q < a.n_peers)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[q] + a.peer_rank), "l"(a.peer_step)
-                                     : "memory");
-            }
-        }
-    }
-}
+#include "iso_lnpost_kernel.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // host side
@@ -302,9 +117,18 @@ int iso_row_grids_fill(iso_ctx *ctx, const iso_grid *mp, const iso_grid *bp, Iso
     return ISO_OK;
 }
 
+// unit-cube rows (BasicStarModel.mnest_prior fused into the evaluation; rng: cube points drawn on the device)
+struct IsoCubeSpec {
+    const double *lo, *hi;   // host arrays [ndim]
+    double *d_pars_out;      // mapped parameters (device or page-locked host memory; NULL: not wanted)
+    unsigned long long seed;
+    long long row0;
+    bool rng;
+};
+
 static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, const iso_grid *bp, const iso_models *models,
                          const int32_t *d_model_of_row, const double *d_pars, int64_t N, double *d_lnpost, double *d_lnprior,
-                         double *d_lnlike, const IsoPeerTargets *peers = nullptr)
+                         double *d_lnlike, const IsoPeerTargets *peers = nullptr, const IsoCubeSpec *cube = nullptr)
 {
     IsoLnpostParams P;
     size_t smem = 0;
@@ -340,55 +164,36 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
             a.peer_flags[q] = peers->flags[q];
         }
     }
-    const bool peer = peers != nullptr;
-    const bool catalog = d_model_of_row != nullptr;
-    int64_t want = (N + ISO_LNPOST_THREADS - 1) / ISO_LNPOST_THREADS;
-    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * ISO_LNPOST_BLOCKS_PER_SM;
-    int blocks = (int)(want < cap ? want : cap);
-    if (blocks < 1) blocks = 1;
-#define ISO_LAUNCH6(NS, CAT, PROF, TRK, PEER, SEQ)                                                                       \
-    do {                                                                                                                 \
-        if (smem > 48 * 1024)                                                                                            \
-            ISO_CUDA(ctx, cudaFuncSetAttribute(iso_lnpost_kernel<NS, CAT, PROF, TRK, PEER, SEQ>,                         \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        iso_lnpost_kernel<NS, CAT, PROF, TRK, PEER, SEQ><<<blocks, ISO_LNPOST_THREADS, smem, st>>>(P);                   \
-    } while (0)
-#define ISO_LAUNCH5(NS, CAT, PROF, TRK, PEER)                                                                            \
-    do {                                                                                                                 \
-        if (NS > 1 && seq) ISO_LAUNCH6(NS, CAT, PROF, TRK, PEER, (NS > 1));                                              \
-        else ISO_LAUNCH6(NS, CAT, PROF, TRK, PEER, false);                                                               \
-    } while (0)
-#define ISO_LAUNCH4(NS, CAT, PROF, TRK)                                                                                  \
-    do {                                                                                                                 \
-        if (peer) ISO_LAUNCH5(NS, CAT, PROF, TRK, true);                                                                 \
-        else ISO_LAUNCH5(NS, CAT, PROF, TRK, false);                                                                     \
-    } while (0)
-#define ISO_LAUNCH2(NS, TRK)                                                           \
-    do {                                                                               \
-        if (catalog) {                                                                 \
-            if (def) ISO_LAUNCH4(NS, true, ISO_PROFILE_DEFAULT, TRK);                  \
-            else ISO_LAUNCH4(NS, true, ISO_PROFILE_GENERIC, TRK);                      \
-        } else {                                                                       \
-            if (def) ISO_LAUNCH4(NS, false, ISO_PROFILE_DEFAULT, TRK);                 \
-            else ISO_LAUNCH4(NS, false, ISO_PROFILE_GENERIC, TRK);                     \
-        }                                                                              \
-    } while (0)
-    const bool def = models->profile_default;
-    const bool track = models->track;
-    const bool seq = bp->dev.ncols == 4;   // multi-star models with at most four bands: the star-sequential kernels
+    IsoLnpostFlags f;
+    f.catalog = d_model_of_row != nullptr;
+    f.profile_default = models->profile_default;
+    f.track = models->track;
+    f.peer = peers != nullptr;
+    f.seq = bp->dev.ncols == 4;   // multi-star models with at most four bands: the star-sequential kernels
+    f.cube = cube != nullptr;
+    a.pars_out = nullptr;
+    a.cube_seed = 0;
+    a.cube_row0 = 0;
+    a.cube_rng = 0;
+    for (int j = 0; j < ISO_MAX_STARS + 4; j++) a.cube_lo[j] = a.cube_w[j] = 0.0;
+    if (cube) {
+        const int ndim = 4 + models->n_stars;
+        for (int j = 0; j < ndim; j++) {
+            a.cube_lo[j] = cube->lo[j];
+            a.cube_w[j] = cube->hi[j] - cube->lo[j];
+        }
+        a.pars_out = cube->d_pars_out;
+        a.cube_seed = cube->seed;
+        a.cube_row0 = cube->row0;
+        a.cube_rng = cube->rng ? 1 : 0;
+    }
     switch (models->n_stars) {
-    case 1:
-        if (track) ISO_LAUNCH2(1, true);
-        else ISO_LAUNCH2(1, false);
-        break;
-    case 2: ISO_LAUNCH2(2, false); break;
-    case 3: ISO_LAUNCH2(3, false); break;
+    case 1: rc = iso_lnpost_dispatch_1(ctx, st, P, smem, f); break;
+    case 2: rc = iso_lnpost_dispatch_2(ctx, st, P, smem, f); break;
+    case 3: rc = iso_lnpost_dispatch_3(ctx, st, P, smem, f); break;
     default: return iso_set_error(ctx, ISO_E_INVALID, "lnpost: bad n_stars");
     }
-#undef ISO_LAUNCH2
-#undef ISO_LAUNCH4
-#undef ISO_LAUNCH5
-#undef ISO_LAUNCH6
+    if (rc != ISO_OK) return rc;
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());
     return ISO_OK;
@@ -421,16 +226,30 @@ static int lnpost_pipe_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int
                          n, (double *)d[2], u->want_prior ? (double *)d[3] : nullptr, u->want_like ? (double *)d[4] : nullptr);
 }
 
-__global__ void iso_mnest_prior_kernel(double *cube, const double *lo, const double *hi, int ndim, long long total)
+// BasicStarModel.mnest_prior (starmodel.py:1637-1640): cube[i] = (hi - lo) * cube[i] + lo, unfused (bit-exact).  The
+// bounds travel in the kernel parameter block: no device allocation or copy per call.
+#define ISO_MNEST_MAX_DIM 16
+struct IsoMnestBounds {
+    double lo[ISO_MNEST_MAX_DIM], w[ISO_MNEST_MAX_DIM];
+};
+
+__global__ void iso_mnest_prior_kernel(double *cube, const __grid_constant__ IsoMnestBounds b, int ndim, long long total)
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        int j = (int)(t % ndim);
-        cube[t] = __dadd_rn(__dmul_rn(hi[j] - lo[j], cube[t]), lo[j]);   // starmodel.py:1637-1640 (unfused, bit-exact)
+        const int j = (int)(t % ndim);
+        double lo = b.lo[0], w = b.w[0];
+#pragma unroll
+        for (int q = 1; q < ISO_MNEST_MAX_DIM; q++)   // constant-bank operands: no dynamic indexing of the parameter block
+            if (q == j) {
+                lo = b.lo[q];
+                w = b.w[q];
+            }
+        cube[t] = __dadd_rn(__dmul_rn(w, cube[t]), lo);
     }
 }
 
 struct MnestUser {
-    const double *d_lo, *d_hi;
+    IsoMnestBounds b;
     int ndim;
 };
 
@@ -444,9 +263,37 @@ static int mnest_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t r
     // in place: the output array aliases the input rows (d[1] receives a device-side copy below)
     // (the buffers are device memory, or page-locked host memory on the small-call path: cudaMemcpyDefault)
     if (d[1] != d[0]) ISO_CUDA(ctx, cudaMemcpyAsync(d[1], d[0], (size_t)total * 8, cudaMemcpyDefault, st));
-    iso_mnest_prior_kernel<<<blocks, 256, 0, st>>>((double *)d[1], u->d_lo, u->d_hi, u->ndim, total);
+    iso_mnest_prior_kernel<<<blocks, 256, 0, st>>>((double *)d[1], u->b, u->ndim, total);
     ctx->launches++;
     ISO_CUDA(ctx, cudaGetLastError());
+    return ISO_OK;
+}
+
+// unit-cube rows through the fused kernel (host-pointer pipeline): d[0] cube in (absent when drawn on the device),
+// d[1] mapped parameters out, d[2..4] lnpost / lnprior / lnlike
+struct CubeUser {
+    const iso_grid *mp, *bp;
+    const iso_models *models;
+    const double *lo, *hi;
+    unsigned long long seed;
+    long long row0;
+    bool rng, want_pars, want_prior, want_like;
+};
+
+static int cube_pipe_launch(iso_ctx *ctx, cudaStream_t st, void *const *d, int64_t row0, int64_t n, void *user)
+{
+    CubeUser *u = (CubeUser *)user;
+    IsoCubeSpec c{u->lo, u->hi, u->want_pars ? (double *)d[1] : nullptr, u->seed, u->row0 + row0, u->rng};
+    return lnpost_launch(ctx, st, u->mp, u->bp, u->models, nullptr, (const double *)d[0], n, (double *)d[2],
+                         u->want_prior ? (double *)d[3] : nullptr, u->want_like ? (double *)d[4] : nullptr, nullptr, &c);
+}
+
+static int check_cube_args(iso_ctx *ctx, const iso_models *models, const double *lo, const double *hi)
+{
+    ISO_REQUIRE(ctx, lo && hi, "unit-cube rows: NULL bounds");
+    ISO_REQUIRE(ctx, models->n_models == 1, "unit-cube rows: one staged model (the bounds are the model's)");
+    for (int j = 0; j < 4 + models->n_stars; j++)
+        ISO_REQUIRE(ctx, lo[j] == lo[j] && hi[j] == hi[j], "unit-cube rows: NaN bound");
     return ISO_OK;
 }
 
@@ -566,26 +413,87 @@ int iso_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *b
 int iso_mnest_prior(iso_ctx *ctx, const double *h_lo, const double *h_hi, int ndim, double *h_cube, int64_t N)
 {
     if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_mnest_prior: ctx is NULL");
-    ISO_REQUIRE(ctx, h_lo && h_hi && ndim >= 1 && ndim <= 64 && N >= 0, "iso_mnest_prior: bad argument");
+    ISO_REQUIRE(ctx, h_lo && h_hi && ndim >= 1 && ndim <= ISO_MNEST_MAX_DIM && N >= 0,
+                "iso_mnest_prior: bad argument (at most 16 parameters)");
     if (N == 0) return ISO_OK;
     ISO_REQUIRE(ctx, h_cube, "iso_mnest_prior: cube is NULL");
-    IsoDeviceGuard guard(ctx->device);
-    double *d_b = nullptr;
-    ISO_CUDA(ctx, cudaMalloc(&d_b, sizeof(double) * 2 * ndim));
-    cudaError_t e = cudaMemcpy(d_b, h_lo, sizeof(double) * ndim, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_b + ndim, h_hi, sizeof(double) * ndim, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(d_b);
-        return iso_check_cuda(ctx, e, "iso_mnest_prior");
+    MnestUser u;
+    memset(&u, 0, sizeof(u));
+    u.ndim = ndim;
+    for (int j = 0; j < ndim; j++) {
+        u.b.lo[j] = h_lo[j];
+        u.b.w[j] = h_hi[j] - h_lo[j];
     }
-    // input and output are the same host array: two pipeline arrays over it (read, then write back)
+    // input and output are the same host array: two pipeline arrays over it (read, then write back); a call of at most
+    // 512 rows (MultiNest transforms one live point at a time) is one launch on page-locked memory + one synchronisation
     IsoPipeArray arr[2];
     arr[0] = IsoPipeArray{h_cube, nullptr, (int64_t)8 * ndim};
     arr[1] = IsoPipeArray{nullptr, h_cube, (int64_t)8 * ndim};
-    MnestUser u{d_b, d_b + ndim, ndim};
-    int rc = iso_run_pipeline(ctx, N, arr, 2, mnest_launch, &u);
-    cudaFree(d_b);
-    return rc;
+    return iso_run_pipeline(ctx, N, arr, 2, mnest_launch, &u);
+}
+
+int iso_mnest_lnpost_batch(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, double *h_cube, int64_t N, double *h_lnpost,
+                           double *h_lnprior, double *h_lnlike)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_mnest_lnpost_batch: ctx is NULL");
+    int rc = iso_check_lnpost_handles(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0, "iso_mnest_lnpost_batch: negative N");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_cube && h_lnpost, "iso_mnest_lnpost_batch: NULL buffer");
+    rc = check_cube_args(ctx, models, h_lo, h_hi);
+    if (rc != ISO_OK) return rc;
+    const int ndim = 4 + models->n_stars;
+    IsoPipeArray arr[5];
+    arr[0] = IsoPipeArray{h_cube, nullptr, (int64_t)8 * ndim};
+    arr[1] = IsoPipeArray{nullptr, h_cube, (int64_t)8 * ndim};   // mapped in place, as mnest_prior leaves the cube
+    arr[2] = IsoPipeArray{nullptr, h_lnpost, 8};
+    arr[3] = IsoPipeArray{nullptr, h_lnprior, 8};
+    arr[4] = IsoPipeArray{nullptr, h_lnlike, 8};
+    CubeUser u{model_pack, bc_pack, models, h_lo, h_hi, 0ULL, 0LL, false, true, h_lnprior != nullptr, h_lnlike != nullptr};
+    return iso_run_pipeline(ctx, N, arr, 5, cube_pipe_launch, &u);
+}
+
+int iso_lnpost_prior_draws(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, uint64_t seed, int64_t row0, int64_t N, double *h_pars,
+                           double *h_lnpost)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_lnpost_prior_draws: ctx is NULL");
+    int rc = iso_check_lnpost_handles(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0 && row0 >= 0, "iso_lnpost_prior_draws: bad argument");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, h_lnpost, "iso_lnpost_prior_draws: NULL buffer");
+    rc = check_cube_args(ctx, models, h_lo, h_hi);
+    if (rc != ISO_OK) return rc;
+    const int ndim = 4 + models->n_stars;
+    IsoPipeArray arr[5];
+    arr[0] = IsoPipeArray{nullptr, nullptr, (int64_t)8 * ndim};   // no input rows: the cube points are drawn on the device
+    arr[1] = IsoPipeArray{nullptr, h_pars, (int64_t)8 * ndim};
+    arr[2] = IsoPipeArray{nullptr, h_lnpost, 8};
+    arr[3] = IsoPipeArray{nullptr, nullptr, 8};
+    arr[4] = IsoPipeArray{nullptr, nullptr, 8};
+    CubeUser u{model_pack, bc_pack, models, h_lo, h_hi, (unsigned long long)seed, (long long)row0, true, h_pars != nullptr, false, false};
+    return iso_run_pipeline(ctx, N, arr, 5, cube_pipe_launch, &u);
+}
+
+int iso_lnpost_cube_device(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
+                           const double *h_lo, const double *h_hi, const double *d_cube, int rng, uint64_t seed, int64_t row0,
+                           int64_t N, double *d_pars, double *d_lnpost)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_lnpost_cube_device: ctx is NULL");
+    int rc = iso_check_lnpost_handles(ctx, model_pack, bc_pack, models);
+    if (rc != ISO_OK) return rc;
+    ISO_REQUIRE(ctx, N >= 0 && row0 >= 0, "iso_lnpost_cube_device: bad argument");
+    if (N == 0) return ISO_OK;
+    ISO_REQUIRE(ctx, d_lnpost && (rng || d_cube), "iso_lnpost_cube_device: NULL buffer");
+    rc = check_cube_args(ctx, models, h_lo, h_hi);
+    if (rc != ISO_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    IsoDeviceGuard guard(ctx->device);
+    IsoCubeSpec c{h_lo, h_hi, d_pars, (unsigned long long)seed, (long long)row0, rng != 0};
+    return lnpost_launch(ctx, ctx->stream, model_pack, bc_pack, models, nullptr, d_cube, N, d_lnpost, nullptr, nullptr, nullptr, &c);
 }
 
 }  // extern "C"

@@ -25,18 +25,42 @@ struct iso_peer_group {
     unsigned *d_done = nullptr;           // CTA arrival counter of the fused kernel
     bool connected = false;
     unsigned long long step = 0;
+    // bounded wait: a rank that does not publish a step within timeout_ns is reported instead of hanging the stream
+    unsigned long long timeout_ns = 10ULL * 1000 * 1000 * 1000;
+    unsigned *h_err = nullptr;            // page-locked, device-mapped: 0, or (missing rank + 1) | (step << 8) of the first timeout
+    unsigned *d_err = nullptr;            // device alias of h_err
 };
 
 // the fused kernel's last CTA publishes the step number in this rank's slot of every rank's flag array (release,
 // system scope); this kernel waits until every rank has published it in ours
-__global__ void iso_peer_wait_kernel(const unsigned long long *own_flags, int n, unsigned long long step)
+//
+// The spin is bounded: lane r gives up when rank r has not published the step within `timeout_ns` of wall-clock time
+// (%globaltimer) and records (r + 1) | (step << 8) in the group's error word (page-locked host memory, first timeout
+// wins); the host turns that into ISO_E_TIMEOUT on its next call / iso_peer_check.  A dead or stalled rank therefore
+// costs one timeout, not a hung stream.
+__device__ __forceinline__ unsigned long long iso_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void iso_peer_wait_kernel(const unsigned long long *own_flags, int n, unsigned long long step,
+                                     unsigned long long timeout_ns, unsigned *err)
 {
     const int r = threadIdx.x;
     if (r < n) {
-        unsigned long long v;
-        do {
+        const unsigned long long t0 = iso_globaltimer();
+        unsigned spins = 0;
+        for (;;) {
+            unsigned long long v;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(own_flags + r) : "memory");
-        } while (v < step);
+            if (v >= step) break;
+            if ((++spins & 255u) == 0 && iso_globaltimer() - t0 > timeout_ns) {
+                atomicCAS_system(err, 0u, (unsigned)(r + 1) | ((unsigned)step << 8));
+                break;
+            }
+        }
     }
     __syncthreads();
     __threadfence_system();
@@ -60,10 +84,38 @@ static void peer_free(iso_peer_group *g)
     if (g->d_recv) cudaFree(g->d_recv);
     if (g->d_flags) cudaFree(g->d_flags);
     if (g->d_done) cudaFree(g->d_done);
+    if (g->h_err) cudaFreeHost(g->h_err);
     delete g;
 }
 
+// the error word of a group -> ISO_E_TIMEOUT (sticky: the receive buffers of a timed-out step are incomplete)
+static int peer_timed_out(iso_ctx *ctx, const iso_peer_group *g)
+{
+    const unsigned e = *(volatile unsigned *)g->h_err;
+    if (!e) return ISO_OK;
+    return iso_set_error(ctx, ISO_E_TIMEOUT, "fused all-gather: rank %u did not publish step %u (mod 2^24) within %.1f s; the "
+                                             "gathered buffer of that step is incomplete",
+                         (e & 0xffu) - 1u, e >> 8, (double)g->timeout_ns * 1e-9);
+}
+
 extern "C" {
+
+int iso_peer_set_timeout(iso_ctx *ctx, iso_peer_group *g, double seconds)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_peer_set_timeout: ctx is NULL");
+    ISO_REQUIRE(ctx, g && seconds > 0.0 && seconds < 1e6, "iso_peer_set_timeout: bad argument");
+    g->timeout_ns = (unsigned long long)(seconds * 1e9);
+    return ISO_OK;
+}
+
+int iso_peer_check(iso_ctx *ctx, iso_peer_group *g)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_peer_check: ctx is NULL");
+    ISO_REQUIRE(ctx, g, "iso_peer_check: group is NULL");
+    IsoDeviceGuard guard(g->device);
+    ISO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return peer_timed_out(ctx, g);
+}
 
 int iso_peer_create(iso_ctx *ctx, int rank, int nranks, int64_t rows_per_rank, iso_peer_group **out)
 {
@@ -81,6 +133,11 @@ int iso_peer_create(iso_ctx *ctx, int rank, int nranks, int64_t rows_per_rank, i
     cudaError_t e = cudaMalloc(&g->d_recv, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_flags, sizeof(unsigned long long) * ISO_MAX_PEERS);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_done, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&g->h_err, sizeof(unsigned), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *g->h_err = 0;
+        e = cudaHostGetDevicePointer((void **)&g->d_err, g->h_err, 0);
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_done, 0, sizeof(unsigned), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_recv, 0, bytes, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_flags, 0, sizeof(unsigned long long) * ISO_MAX_PEERS, ctx->stream);
@@ -137,6 +194,10 @@ int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const 
     ISO_REQUIRE(ctx, g && g->connected, "iso_lnpost_allgather_device: peer group not connected");
     ISO_REQUIRE(ctx, g->device == ctx->device, "iso_lnpost_allgather_device: peer group belongs to another device");
     ISO_REQUIRE(ctx, N >= 0 && N <= g->pad, "iso_lnpost_allgather_device: more rows than the group was created for");
+    {
+        int trc = peer_timed_out(ctx, g);
+        if (trc != ISO_OK) return trc;
+    }
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     IsoDeviceGuard guard(ctx->device);
     const unsigned long long step = ++g->step;
@@ -161,7 +222,7 @@ int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const 
         iso_peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(t);
         ctx->launches += 1;
     }
-    iso_peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_flags, g->nranks, step);
+    iso_peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_flags, g->nranks, step, g->timeout_ns, g->d_err);
     ctx->launches += 1;
     ISO_CUDA(ctx, cudaGetLastError());
     if (d_gathered) *d_gathered = g->d_recv + half;

@@ -13,6 +13,7 @@
 // fill the GPU.  Randomness is counter-based (Philox4x32-10 keyed by seed, counter = step / half / walker / chain),
 // so a run is reproducible and independent of scheduling; tests replay the same stream on the host.
 #include "iso_lnpost_row.cuh"
+#include "iso_stretch.cuh"
 
 struct iso_sampler {
     const iso_grid *mp = nullptr, *bp = nullptr;
@@ -25,6 +26,8 @@ struct iso_sampler {
     double *d_pos = nullptr;        // [n_chains, n_walkers, ndim]
     double *d_lnprob = nullptr;     // [n_chains, n_walkers]
     unsigned long long *d_acc = nullptr;   // [n_chains] accepted proposals
+    long long step_acc0 = 0;        // value of `step` when the acceptance counters were last zeroed (iso_sampler_reset)
+    double *d_mom = nullptr;        // [n_chains, 2 ndim + 1] running sums of the kept samples: sum x_d, sum x_d^2, count
 };
 
 struct IsoSamplerParams {
@@ -38,34 +41,9 @@ struct IsoSamplerParams {
     double *pos, *lnprob;
     double *chain_out, *lnprob_out;   // [n_steps / thin, n_chains, n_walkers, (ndim)] or NULL
     unsigned long long *accepted;
+    double *moments;                  // [n_chains, 2 ndim + 1] (see iso_sampler) or NULL
     IsoModelDev model;                // the single model (n_models == 1)
 };
-
-__device__ __forceinline__ void iso_philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
-                                                  unsigned (&out)[4])
-{
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0;
-    out[1] = c1;
-    out[2] = c2;
-    out[3] = c3;
-}
-
-// 53-bit uniform in [0, 1) from two 32-bit words
-__device__ __forceinline__ double iso_u01(unsigned hi, unsigned lo)
-{
-    return (double)((((unsigned long long)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
-}
 
 // BOUNDS = 512: ensembles of up to 1024 walkers, 128 registers per thread, several CTAs per SM (many chains in flight);
 // BOUNDS = 128: ensembles of up to 256 walkers when the chains do not fill the GPU anyway — one chain is bound by the
@@ -89,10 +67,10 @@ __global__ void __launch_bounds__(BOUNDS, 1) iso_sampler_kernel(const __grid_con
 
     for (int i = t; i < P.n_walkers * NDIMP; i += blockDim.x) s_pos[i] = g_pos[i];
     for (int i = t; i < P.n_walkers; i += blockDim.x) s_lp[i] = g_lp[i];
-    iso_stage_axis_tables(P.G, s_nodes);   // ends with __syncthreads()
+    iso_stage_axis_tables(P.G, s_nodes);   // ends with a wait on the tables' mbarrier, which orders nothing else:
+    __syncthreads();                       // the ensemble in shared memory is complete before the first proposal reads it
 
     unsigned long long n_acc = 0;
-    const unsigned k0 = (unsigned)(P.seed & 0xffffffffu), k1 = (unsigned)(P.seed >> 32);
     for (int s = 0; s < P.n_steps; s++) {
         const unsigned long long gstep = (unsigned long long)(P.step0 + s);
 #pragma unroll 1
@@ -100,25 +78,10 @@ __global__ void __launch_bounds__(BOUNDS, 1) iso_sampler_kernel(const __grid_con
             if (t < nhalf) {
                 const int k = half * nhalf + t;            // walker being moved
                 const int other0 = (1 - half) * nhalf;     // first walker of the complementary half
-                unsigned r[4], r2[4];
-                const unsigned ctr0 = (unsigned)(gstep * 2 + half), ctr1 = (unsigned)((gstep * 2 + half) >> 32);
-                iso_philox4x32_10(ctr0, ctr1 ^ ((unsigned)chain << 8), (unsigned)k, 0u, k0, k1, r);
-                iso_philox4x32_10(ctr0, ctr1 ^ ((unsigned)chain << 8), (unsigned)k, 1u, k0, k1, r2);
-                const double u = iso_u01(r[0], r[1]);
-                const int j = other0 + (int)(r[2] % (unsigned)nhalf);
-                const double u_acc = iso_u01(r2[0], r2[1]);
-                // z = ((a - 1) u + 1)^2 / a — unfused so that a host replay of the stream is bit-identical
-                const double zr = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-                const double z = __ddiv_rn(__dmul_rn(zr, zr), P.a);
-                double q[NDIMP];
-#pragma unroll
-                for (int d = 0; d < NDIMP; d++) {
-                    const double c = s_pos[j * NDIMP + d], x = s_pos[k * NDIMP + d];
-                    q[d] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), z));
-                }
+                double q[NDIMP], z, u_acc;
+                iso_stretch_propose<NDIMP>(P.seed, gstep, half, chain, k, other0, nhalf, P.a, s_pos, q, z, u_acc);
                 const IsoRowResult res = iso_lnpost_row<NSTARS, PROFILE, TRACK>(P.G, s_nodes, m, q, false, false);
-                const double lnpdiff = (NDIMP - 1) * log(z) + res.lnpost - s_lp[k];
-                if (lnpdiff > log(u_acc)) {   // NaN compares false: a NaN lnpost (BC grid out of range) is a rejection
+                if (iso_stretch_accept<NDIMP>(z, u_acc, res.lnpost, s_lp[k])) {
 #pragma unroll
                     for (int d = 0; d < NDIMP; d++) s_pos[k * NDIMP + d] = q[d];
                     s_lp[k] = res.lnpost;
@@ -137,6 +100,30 @@ __global__ void __launch_bounds__(BOUNDS, 1) iso_sampler_kernel(const __grid_con
                 double *o = P.lnprob_out + ((size_t)keep * P.n_chains + chain) * P.n_walkers;
                 for (int i = t; i < P.n_walkers; i += blockDim.x) o[i] = s_lp[i];
             }
+            if (P.moments) {
+                // running first / second moments of every kept ensemble (posterior mean and spread per chain without
+                // the samples ever leaving the GPU — what a catalog fit gathers per star): warp sums, one atomic per warp
+                double *mom = P.moments + (size_t)chain * (2 * NDIMP + 1);
+#pragma unroll
+                for (int d = 0; d < NDIMP; d++) {
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int w = t; w < P.n_walkers; w += blockDim.x) {
+                        const double x = s_pos[w * NDIMP + d];
+                        s1 += x;
+                        s2 = fma(x, x, s2);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if ((t & 31) == 0) {
+                        atomicAdd(mom + d, s1);
+                        atomicAdd(mom + NDIMP + d, s2);
+                    }
+                }
+                if (t == 0) atomicAdd(mom + 2 * NDIMP, (double)P.n_walkers);
+            }
         }
     }
     for (int i = t; i < P.n_walkers * NDIMP; i += blockDim.x) g_pos[i] = s_pos[i];
@@ -150,6 +137,7 @@ static void sampler_free(iso_sampler *s)
     if (s->d_pos) cudaFree(s->d_pos);
     if (s->d_lnprob) cudaFree(s->d_lnprob);
     if (s->d_acc) cudaFree(s->d_acc);
+    if (s->d_mom) cudaFree(s->d_mom);
     delete s;
 }
 
@@ -185,6 +173,9 @@ int iso_sampler_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid 
     if (e == cudaSuccess) e = cudaMalloc(&s->d_lnprob, n_rows * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_acc, n_chains * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_acc, 0, n_chains * sizeof(unsigned long long), ctx->stream);
+    const size_t mom_bytes = (size_t)n_chains * (2 * s->ndim + 1) * sizeof(double);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_mom, mom_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_mom, 0, mom_bytes, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(s->d_pos, h_p0, n_rows * s->ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     int *d_mor = nullptr;
@@ -204,9 +195,24 @@ int iso_sampler_create(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid 
     rc = iso_lnpost_batch_device(ctx, model_pack, bc_pack, models, d_mor, s->d_pos, (int64_t)n_rows, s->d_lnprob, nullptr, nullptr);
     e = cudaStreamSynchronize(ctx->stream);
     if (d_mor) cudaFree(d_mor);
+    // a NaN initial lnpost (a walker whose star falls off the BC grid) can never be left — every proposal compares
+    // against NaN — and emcee refuses such an ensemble ("The initial lnprob was NaN"); -inf walkers are legal
+    long long first_nan = -1;
+    if (rc == ISO_OK && e == cudaSuccess) {
+        std::vector<double> lp(n_rows);
+        e = cudaMemcpy(lp.data(), s->d_lnprob, n_rows * sizeof(double), cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < n_rows && first_nan < 0; i++)
+            if (lp[i] != lp[i]) first_nan = (long long)i;
+    }
     if (rc != ISO_OK || e != cudaSuccess) {
         sampler_free(s);
         return rc != ISO_OK ? rc : iso_check_cuda(ctx, e, "iso_sampler_create");
+    }
+    if (first_nan >= 0) {
+        sampler_free(s);
+        return iso_set_error(ctx, ISO_E_INVALID, "iso_sampler_create: the initial lnpost of walker %lld of chain %lld is NaN "
+                                                 "(outside the bolometric-correction grid); draw another starting point",
+                             first_nan % n_walkers, first_nan / n_walkers);
     }
     *out = s;
     return ISO_OK;
@@ -252,6 +258,7 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     P.chain_out = d_chain;
     P.lnprob_out = d_lp;
     P.accepted = s->d_acc;
+    P.moments = (thin >= 1 && n_keep > 0) ? s->d_mom : nullptr;
     int threads = ((s->n_walkers / 2 + 31) / 32) * 32;
     // few chains of small ensembles: the latency-optimised instantiation (see the kernel's comment)
     const bool few_small = threads <= 128 && s->n_chains <= ctx->prop.multiProcessorCount;
@@ -318,7 +325,32 @@ int iso_sampler_state(iso_ctx *ctx, iso_sampler *s, double *h_pos, double *h_lnp
     ISO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_accepted)   // [n_chains]
         for (int c = 0; c < s->n_chains; c++) n_accepted[c] = (int64_t)acc[c];
-    if (n_proposed) *n_proposed = (int64_t)s->step * s->n_walkers;   // per chain
+    if (n_proposed) *n_proposed = (int64_t)(s->step - s->step_acc0) * s->n_walkers;   // per chain, since the last reset
+    return ISO_OK;
+}
+
+int iso_sampler_reset(iso_ctx *ctx, iso_sampler *s)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_sampler_reset: ctx is NULL");
+    ISO_REQUIRE(ctx, s, "iso_sampler_reset: sampler is NULL");
+    IsoDeviceGuard guard(s->device);
+    ISO_CUDA(ctx, cudaMemsetAsync(s->d_acc, 0, s->n_chains * sizeof(unsigned long long), ctx->stream));
+    ISO_CUDA(ctx, cudaMemsetAsync(s->d_mom, 0, (size_t)s->n_chains * (2 * s->ndim + 1) * sizeof(double), ctx->stream));
+    s->step_acc0 = s->step;
+    return ISO_OK;
+}
+
+int iso_sampler_moments(iso_ctx *ctx, iso_sampler *s, double *h_moments, const double **d_moments)
+{
+    if (!ctx) return iso_set_error(nullptr, ISO_E_INVALID, "iso_sampler_moments: ctx is NULL");
+    ISO_REQUIRE(ctx, s, "iso_sampler_moments: sampler is NULL");
+    IsoDeviceGuard guard(s->device);
+    if (d_moments) *d_moments = s->d_mom;
+    if (h_moments) {
+        ISO_CUDA(ctx, cudaMemcpyAsync(h_moments, s->d_mom, (size_t)s->n_chains * (2 * s->ndim + 1) * sizeof(double),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        ISO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return ISO_OK;
 }
 

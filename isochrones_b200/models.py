@@ -270,7 +270,7 @@ class ModelGridInterpolator(object):
             self.ctx.handle, self.model_pack.handle, bc.handle, _lib.ip(io), 0, 1, 2, 3, _lib.ip(bc_cols), len(bands), ptrs,
             int(n), d_Teff, d_logg, d_feh, d_mags))
 
-    def get_eep(self, mass, age, feh, accurate=False, return_nan=True):
+    def get_eep(self, mass, age, feh, accurate=False, **kwargs):
         """EEP of stars of given (mass, log10 age, feh).  Scalars give a float, anything else is broadcast.
 
         Evolution-track grids: the fast bracketing interpolation ``interp_eep(s)`` of the reference (interp.py:488-558,
@@ -279,7 +279,9 @@ class ModelGridInterpolator(object):
         reference runs one scipy Nelder-Mead minimisation per star on the host (models.py:544-578), this brackets the
         root for ALL stars at once by repeated 64-way subdivision of the EEP range — three interpolation launches of
         ``64 N`` points — and finishes with the secant of the last bracket (:meth:`solve_eep`).  Stars without a root
-        give NaN (``return_nan=False``: raise, like the reference)."""
+        give NaN (``return_nan=False``: raise, like the reference; the reference's optimiser keywords are accepted and
+        have no meaning here)."""
+        return_nan = kwargs.pop("return_nan", True)
         scalar = all(isinstance(v, (float, int)) for v in (mass, age, feh))
         b = np.broadcast(mass, age, feh)
         mass_a, age_a, feh_a = [np.ascontiguousarray(np.atleast_1d(np.resize(x, b.shape)).astype(float).ravel())
@@ -329,24 +331,41 @@ class ModelGridInterpolator(object):
             frac = np.where(f_hi > f_lo, -f_lo / (f_hi - f_lo), 0.0)
         return np.where(alive, lo + frac * (hi - lo), np.nan)
 
-    def generate(self, mass, age, feh, distance=10.0, AV=0.0, bands=None, eeps=None):
-        """Forward-simulate stars of given (mass, log10 age, feh) on an evolution-track grid: ``get_eep`` -> every
-        model-grid column + apparent magnitudes at (distance, AV), one row per star (what the reference's ``generate``
-        models.py:580-629 is used for by the synthetic-observation callers of §8f-3).  Three kernel launches for the
-        whole batch; returns the frame of ``__call__`` plus the requested (mass, age, feh)."""
-        if eeps is None:
-            eeps = self.get_eep(mass, age, feh)
-        saved = self.bands
-        try:
-            if bands is not None:
-                self.bands = list(bands)
-            frame = self(mass, eeps, feh, distance=distance, AV=AV)
-        finally:
-            self.bands = saved
-        n = len(frame)
-        for name, v in (("distance", distance), ("AV", AV), ("initial_feh", feh), ("requested_age", age)):
-            frame[name] = np.broadcast_to(np.asarray(v, dtype=float), (n,))
-        return frame
+    def generate(self, mass, age, feh, props="all", bands=None, eeps=None, return_df=True, return_dict=False,
+                 distance=10, AV=0, all_As=False, **kwargs):
+        """Forward-simulate stars of given (mass, log10 age, feh) on an evolution-track grid — the reference's
+        ``generate`` (models.py:580-629; same signature and outputs) as three batched launches: ``get_eep``, one
+        ``interp_value`` over the requested model-grid columns, one ``interp_mag`` at (distance, AV).
+
+        Output: a DataFrame (default), a dict of columns (``return_dict``) or the bare ``[N, n_props + n_bands]``
+        array (``return_df=False``); frames / dicts also carry ``distance``, ``AV``, ``initial_feh``,
+        ``requested_age`` and, with ``all_As``, the per-band extinction ``A_<band>`` (magnitude minus its AV = 0
+        value)."""
+        mass, age, feh, distance, AV = [np.asarray(x, dtype=float) for x in (mass, age, feh, distance, AV)]
+        shape = np.broadcast(mass, age, feh, distance, AV).shape
+        flat = [np.ascontiguousarray(np.broadcast_to(x, shape)).reshape(-1) for x in (mass, age, feh, distance, AV)]
+        m, a, f, d, av = flat
+        bands = list(self.bands if bands is None else bands)
+        e = self.get_eep(m, a, f, **kwargs) if eeps is None else np.broadcast_to(np.asarray(eeps, dtype=float), shape).reshape(-1)
+        names = list(self.model_grid.interp.columns) if isinstance(props, str) and props == "all" else list(props)
+        table = {}
+        if names:
+            table.update(zip(names, self.interp_value([m, e, f], names).T))
+        if bands:
+            mags = self.interp_mag([m, e, f, d, av], bands)[3]
+            table.update(("{}_mag".format(b), mags[:, j]) for j, b in enumerate(bands))
+        if not (return_df or return_dict):
+            out = np.column_stack(list(table.values())) if table else np.empty((len(m), 0))
+            return out[0] if shape == () else out
+        table.update(distance=d, AV=av, initial_feh=f, requested_age=a)
+        if all_As and bands:
+            clear = self.interp_mag([m, e, f, d, np.zeros_like(av)], bands)[3]
+            table.update(("A_{}".format(b), table["{}_mag".format(b)] - clear[:, j]) for j, b in enumerate(bands))
+        if return_dict:
+            return {k: (v[0] if shape == () else v) for k, v in table.items()}
+        import pandas as pd
+
+        return pd.DataFrame(table)
 
     def __call__(self, p1, p2, p3, distance=10.0, AV=0.0):
         """All model-grid columns + magnitudes as a DataFrame (models.py:471-482) — same kernels, wider output."""

@@ -110,6 +110,82 @@ def file_exchange(path, rank, timeout=120.0):
     return exchange
 
 
+class FileRendezvous(object):
+    """Launcher-agnostic plumbing for the ranks of ONE node through a directory every rank can see: byte all-gather,
+    broadcast, barrier and a max-reduction of a float.  Each operation has a sequence number; a rank publishes
+    ``<seq>.<rank>`` atomically (write + rename) and polls for the others.  Only setup and the gaps between timed
+    regions go through it (handle / unique-id exchange, timing reductions) — never the data path.
+
+    ``from_env()`` builds the directory name from the launcher's environment (``RANK`` / ``WORLD_SIZE`` as torchrun,
+    mpirun wrappers or a plain shell loop export them): ``$ISO_B200_RDZV`` when set, else a name derived from the
+    launching process (the ranks of one launch share their parent) and ``MASTER_PORT``."""
+
+    def __init__(self, path, rank, world, timeout=300.0):
+        self.path, self.rank, self.world, self.timeout = path, int(rank), int(world), float(timeout)
+        self.seq = 0
+        os.makedirs(path, exist_ok=True)
+
+    @classmethod
+    def from_env(cls, timeout=300.0):
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        path = os.environ.get("ISO_B200_RDZV")
+        if not path:
+            import tempfile
+
+            path = os.path.join(tempfile.gettempdir(), "iso_b200_rdzv_%d_%s_%s" % (
+                os.getuid(), os.environ.get("MASTER_PORT", "0"), os.getppid()))
+        return cls(path, rank, world, timeout)
+
+    def allgather_bytes(self, payload):
+        """``payload -> [payload of rank 0, payload of rank 1, ...]``."""
+        self.seq += 1
+        mine = os.path.join(self.path, "%06d.%d" % (self.seq, self.rank))
+        with open(mine + ".tmp", "wb") as f:
+            f.write(payload)
+        os.replace(mine + ".tmp", mine)
+        out, t0 = [], time.time()
+        for r in range(self.world):
+            name = os.path.join(self.path, "%06d.%d" % (self.seq, r))
+            while not os.path.exists(name):
+                if time.time() - t0 > self.timeout:
+                    raise TimeoutError("rank %d: rank %d did not reach rendezvous step %d in %s" % (self.rank, r, self.seq, self.path))
+                time.sleep(0.0005)
+            with open(name, "rb") as f:
+                out.append(f.read())
+        return out
+
+    def broadcast(self, payload):
+        """Rank 0's payload on every rank (``exchange`` of ``NcclGather``)."""
+        return self.allgather_bytes(payload if self.rank == 0 else b"")[0]
+
+    def barrier(self):
+        self.allgather_bytes(b"")
+
+    def max(self, x):
+        return max(float(v) for v in self.allgather_bytes(repr(float(x)).encode()))
+
+    def all(self, flag):
+        return all(v == b"1" for v in self.allgather_bytes(b"1" if flag else b"0"))
+
+    def close(self):
+        """Every rank signs off; rank 0 removes the directory once all have (best effort)."""
+        try:
+            self.barrier()
+            if self.rank != 0:
+                open(os.path.join(self.path, "done.%d" % self.rank), "wb").close()
+                return
+            import shutil
+
+            t0 = time.time()
+            while not all(os.path.exists(os.path.join(self.path, "done.%d" % r)) for r in range(1, self.world)):
+                if time.time() - t0 > 10.0:
+                    break
+                time.sleep(0.001)
+            shutil.rmtree(self.path, ignore_errors=True)
+        except Exception:
+            pass
+
+
 class NcclGather(object):
     """All-gather of float64 device buffers across the ranks' contexts (``iso_nccl_init`` / ``iso_allgather_f64``)."""
 
@@ -166,6 +242,15 @@ class PeerGather(object):
             self.ctx.handle, compiled.model_pack.handle, compiled.bc_pack.handle, compiled.handle, d_model_of_row, d_pars,
             int(n), self.handle, C.byref(out)))
         return out
+
+    def set_timeout(self, seconds):
+        """Bound of the per-step completion wait (default 10 s): a rank that does not publish a step in time makes
+        the next call / ``check()`` raise ``IsoError`` (``ISO_E_TIMEOUT``) instead of hanging the stream."""
+        self.ctx.check(_lib.lib().iso_peer_set_timeout(self.ctx.handle, self.handle, float(seconds)))
+
+    def check(self):
+        """Synchronise the stream and raise if a step timed out."""
+        self.ctx.check(_lib.lib().iso_peer_check(self.ctx.handle, self.handle))
 
     def close(self):
         if self.handle:

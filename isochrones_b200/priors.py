@@ -100,8 +100,10 @@ class Prior(object):
         out.self = self._leaf_struct()
         return out
 
+    _owner = None   # the interpolator of the model that holds this prior (BasicStarModel sets it): its context evaluates
+
     def _on_device(self, x, which):
-        ctx = _lib.default_context()
+        ctx = self._owner.ctx if self._owner is not None else _lib.default_context()
         flat = _lib.f64(np.atleast_1d(x)).ravel()
         res = np.empty_like(flat)
         image = self.to_struct()

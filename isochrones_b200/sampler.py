@@ -55,8 +55,29 @@ class DeviceEnsembleSampler(object):
         return self.state()[:2]
 
     def reset(self):
-        """Forget the stored samples (walker positions are kept), as ``emcee.EnsembleSampler.reset``."""
+        """Forget the stored samples, the acceptance counters and the running moments (walker positions are kept), as
+        ``emcee.EnsembleSampler.reset`` — ``acceptance_fraction`` after a burn-in + ``reset`` describes the production
+        run only."""
         self._chains, self._lnprobs = [], []
+        self.ctx.check(_lib.lib().iso_sampler_reset(self.ctx.handle, self.handle))
+
+    def moments(self):
+        """Posterior mean and standard deviation per chain and parameter from the running sums the kernel keeps over
+        every kept (thinned) ensemble since the last ``reset``: ``(mean[n_chains, ndim], std[n_chains, ndim], count)``
+        — the samples themselves never leave the GPU."""
+        m = np.empty((self.n_chains, 2 * self.ndim + 1))
+        self.ctx.check(_lib.lib().iso_sampler_moments(self.ctx.handle, self.handle, _lib.dp(m), None))
+        cnt = m[:, -1]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = m[:, :self.ndim] / cnt[:, None]
+            var = m[:, self.ndim:2 * self.ndim] / cnt[:, None] - mean ** 2
+        return mean, np.sqrt(np.maximum(var, 0.0)), cnt
+
+    def moments_device(self):
+        """Device pointer of the raw running sums ``[n_chains, 2 ndim + 1]`` (send buffer of a multi-GPU gather)."""
+        p = C.c_void_p()
+        self.ctx.check(_lib.lib().iso_sampler_moments(self.ctx.handle, self.handle, None, C.byref(p)))
+        return p
 
     def state(self):
         pos = np.empty((self.n_chains, self.n_walkers, self.ndim))
@@ -103,6 +124,85 @@ class DeviceEnsembleSampler(object):
     def close(self):
         if self.handle:
             _lib.lib().iso_sampler_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedEnsembleSampler(object):
+    """ONE ensemble of walkers sharded over the GPUs of a node (``iso_ensemble_*``): every rank (one process per GPU)
+    constructs this with the SAME ``p0`` and ``seed``; per half-step a rank moves only its block of the active half and
+    its kernel writes every accepted walker into the ensemble copy of every rank over NVLink peer mappings — the
+    acceptance step's exchange fused into the evaluation, no collective launch.  The chain is the one
+    ``DeviceEnsembleSampler`` produces for the same seed, bit for bit, whatever the number of ranks; ensembles are not
+    bounded by shared memory (1e5 - 1e6 walkers).
+
+    ``allgather_bytes``: ``payload -> [payload of every rank]`` (``parallel.FileRendezvous.allgather_bytes``, a
+    torch.distributed / MPI wrapper, ..); ignored for a single rank."""
+
+    def __init__(self, compiled, n_walkers, p0, seed=0, a=2.0, rank=0, world=1, allgather_bytes=None):
+        self.compiled, self.ctx, self.ndim = compiled, compiled.ctx, compiled.ndim
+        self.rank, self.world, self.n_walkers = int(rank), int(world), int(n_walkers)
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        if p0.shape != (self.n_walkers, self.ndim):
+            raise ValueError("p0 must be [n_walkers=%d, ndim=%d], got %r" % (self.n_walkers, self.ndim, p0.shape))
+        self.handle = C.c_void_p()
+        L = _lib.lib()
+        self.ctx.check(L.iso_ensemble_create(
+            self.ctx.handle, compiled.model_pack.handle, compiled.bc_pack.handle, compiled.handle, self.n_walkers,
+            _lib.dp(p0), C.c_uint64(int(seed)), float(a), self.rank, self.world, C.byref(self.handle)))
+        if self.world > 1:
+            buf = C.create_string_buffer(128)
+            self.ctx.check(L.iso_ensemble_export(self.ctx.handle, self.handle, buf))
+            handles = allgather_bytes(bytes(buf.raw))
+            if len(handles) != self.world or any(len(h) != 128 for h in handles):
+                raise ValueError("the handle exchange must return one 128-byte payload per rank")
+            blob = C.create_string_buffer(b"".join(handles), 128 * self.world)
+            self.ctx.check(L.iso_ensemble_connect(self.ctx.handle, self.handle, blob))
+        self._chains, self._lnprobs = [], []
+        self.n_steps = 0
+
+    def set_timeout(self, seconds):
+        self.ctx.check(_lib.lib().iso_ensemble_set_timeout(self.ctx.handle, self.handle, float(seconds)))
+
+    def run_mcmc(self, n_steps, thin=1, store=True):
+        """Advance the ensemble by ``n_steps`` steps (every rank calls this with the same arguments); ``store`` keeps
+        the thinned chain on THIS rank.  Returns ``(pos[n_walkers, ndim], lnprob[n_walkers])``."""
+        n_keep = n_steps // thin
+        chain = np.empty((n_keep, self.n_walkers, self.ndim)) if store else None
+        lnp = np.empty((n_keep, self.n_walkers)) if store else None
+        self.ctx.check(_lib.lib().iso_ensemble_run(self.ctx.handle, self.handle, int(n_steps), int(thin),
+                                                   _lib.dp(chain) if store else None, _lib.dp(lnp) if store else None))
+        if store:
+            self._chains.append(chain)
+            self._lnprobs.append(lnp)
+        self.n_steps += n_steps
+        return self.state()[:2]
+
+    def state(self):
+        """``(pos, lnprob, proposals accepted by this rank, proposals per ensemble)``."""
+        pos, lnp = np.empty((self.n_walkers, self.ndim)), np.empty(self.n_walkers)
+        acc, prop = C.c_int64(), C.c_int64()
+        self.ctx.check(_lib.lib().iso_ensemble_state(self.ctx.handle, self.handle, _lib.dp(pos), _lib.dp(lnp), C.byref(acc),
+                                                     C.byref(prop)))
+        return pos, lnp, acc.value, prop.value
+
+    @property
+    def chains(self):
+        """``[n_kept, n_walkers, ndim]``"""
+        return np.concatenate(self._chains, axis=0) if self._chains else np.empty((0, self.n_walkers, self.ndim))
+
+    @property
+    def lnprobs(self):
+        return np.concatenate(self._lnprobs, axis=0) if self._lnprobs else np.empty((0, self.n_walkers))
+
+    def close(self):
+        if self.handle:
+            _lib.lib().iso_ensemble_destroy(self.ctx.handle, self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

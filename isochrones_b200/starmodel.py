@@ -23,16 +23,25 @@ class CompiledModel(object):
     """Device image of one or more star models that share an interpolator (catalog mode: one per star)."""
 
     def __init__(self, ic, structs, bands_key):
+        self._stage(ic, (_lib.IsoModel * len(structs))(*structs), len(structs), structs[0].n_stars, bands_key)
+
+    @classmethod
+    def from_struct_array(cls, ic, arr, n_models, n_stars, bands_key):
+        """From a ready ctypes array of ``iso_model`` (the catalog driver packs thousands of stars vectorised)."""
+        self = cls.__new__(cls)
+        self._stage(ic, arr, n_models, n_stars, bands_key)
+        return self
+
+    def _stage(self, ic, arr, n_models, n_stars, bands_key):
         self.ic = ic
         self.ctx = ic.ctx
-        self.n_models = len(structs)
-        self.n_stars = structs[0].n_stars
+        self.n_models = int(n_models)
+        self.n_stars = int(n_stars)
         self.ndim = 4 + self.n_stars
         self.model_pack = ic.model_pack
-        self.bc_pack = ic.bc_pack(bands_key)
-        arr = (_lib.IsoModel * len(structs))(*structs)
+        self.bc_pack = ic.bc_pack(tuple(bands_key))
         self.handle = C.c_void_p()
-        self.ctx.check(_lib.lib().iso_models_stage(self.ctx.handle, arr, len(structs), C.byref(self.handle)))
+        self.ctx.check(_lib.lib().iso_models_stage(self.ctx.handle, arr, self.n_models, C.byref(self.handle)))
         self._one = threading.local()   # per-thread buffers of the scalar call
 
     def lnpost_one(self, p, parts=False):
@@ -154,6 +163,8 @@ class BasicStarModel(object):
         self._priors = {"mass": ChabrierPrior(), "feh": FehPrior(), "age": AgePrior(),
                         "distance": DistancePrior(), "AV": AVPrior()}
         self._priors["eep"] = EEP_prior(self.ic, self._priors[self.ic.eep_replaces], bounds=eep_bounds)
+        for pr in self._priors.values():
+            pr._owner = self.ic      # stand-alone evaluations (prior.lnpdf(x)) run on the model's own GPU context
         self._bounds = {"mass": None, "feh": None, "age": None, "distance": DistancePrior().bounds,
                         "AV": AVPrior().bounds, "eep": self._priors["eep"].bounds}
         # Reset bounds to match IC bounds (starmodel.py:1458-1460)
@@ -172,6 +183,7 @@ class BasicStarModel(object):
                     self.set_bounds(distance=(0, 1.0 / np.abs(unc) * 2000))
         if halo_fraction is not None:
             self._priors["feh"] = FehPrior(halo_fraction=halo_fraction)
+            self._priors["feh"]._owner = self.ic
 
         self._directory = str(directory)
         self._samples = None
@@ -234,6 +246,7 @@ class BasicStarModel(object):
         for prop, prior in kwargs.items():
             self._priors[prop] = prior
             self._bounds[prop] = prior.bounds
+            prior._owner = self.ic
         self._compiled = None
 
     def prior(self, prop, val, **kwargs):
@@ -308,8 +321,7 @@ class BasicStarModel(object):
 
     def mnest_prior(self, cube, ndim=None, nparams=None):
         """Unit cube -> parameter box, in place (starmodel.py:1637-1640); ``cube`` may be ``[ndim]`` or ``[N, ndim]``."""
-        lo = np.array([self.bounds(par)[0] for par in self.param_names], dtype=np.float64)
-        hi = np.array([self.bounds(par)[1] for par in self.param_names], dtype=np.float64)
+        lo, hi = self._box()
         arr = np.asarray(cube)
         direct = isinstance(cube, np.ndarray) and arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
         work = arr if direct else np.ascontiguousarray([cube[i] for i in range(len(lo))], dtype=np.float64)
@@ -323,6 +335,45 @@ class BasicStarModel(object):
     def mnest_loglike(self, cube, ndim=None, nparams=None):
         n = self.n_params
         return self.lnpost([cube[i] for i in range(n)])
+
+    def _box(self):
+        lo = np.array([self.bounds(par)[0] for par in self.param_names], dtype=np.float64)
+        hi = np.array([self.bounds(par)[1] for par in self.param_names], dtype=np.float64)
+        return lo, hi
+
+    def mnest_lnpost_batch(self, cube, parts=False):
+        """``mnest_prior`` + ``mnest_loglike`` (starmodel.py:1637-1645) of a whole set of live points in ONE launch:
+        ``cube[N, ndim]`` (float64, C-contiguous) holds unit-cube points on entry and the mapped parameters on return —
+        exactly what ``mnest_prior`` leaves in MultiNest's cube — and the returned ``lnpost[N]`` is ``mnest_loglike`` of
+        every row (``parts``: also lnprior and lnlike).  ``iso_mnest_lnpost_batch``."""
+        if not (isinstance(cube, np.ndarray) and cube.dtype == np.float64 and cube.flags["C_CONTIGUOUS"]
+                and cube.ndim == 2 and cube.shape[1] == self.n_params):
+            raise ValueError("cube must be a C-contiguous float64 array of shape [N, %d] (it is mapped in place)" % self.n_params)
+        lo, hi = self._box()
+        c = self.compiled
+        n = cube.shape[0]
+        lnpost = np.empty(n)
+        lnprior = np.empty(n) if parts else None
+        lnlike = np.empty(n) if parts else None
+        c.ctx.check(_lib.lib().iso_mnest_lnpost_batch(
+            c.ctx.handle, c.model_pack.handle, c.bc_pack.handle, c.handle, _lib.dp(lo), _lib.dp(hi), _lib.dp(cube), n,
+            _lib.dp(lnpost), _lib.dp(lnprior) if parts else None, _lib.dp(lnlike) if parts else None))
+        return (lnpost, lnprior, lnlike) if parts else lnpost
+
+    def prior_box_draws(self, n, seed=0, row0=0, return_pars=True, out=None):
+        """``n`` uniform draws from the parameter box (``bounds`` of every parameter) evaluated on the device where they
+        are made (``iso_lnpost_prior_draws``): nothing is shipped per row.  Row ``i`` is the Philox4x32-10 point of
+        counter ``row0 + i`` under ``seed`` — the same rows whatever the batch split or the number of GPUs.  Returns
+        ``(pars[n, ndim], lnpost[n])`` or just ``lnpost`` (``return_pars=False``); the live-point / walker
+        initialisation of ``sample_from_prior`` (starmodel.py:1716-1748) keeps the finite ones."""
+        lo, hi = self._box()
+        c = self.compiled
+        lnpost = out if out is not None else np.empty(n)
+        pars = np.empty((n, self.n_params)) if return_pars else None
+        c.ctx.check(_lib.lib().iso_lnpost_prior_draws(
+            c.ctx.handle, c.model_pack.handle, c.bc_pack.handle, c.handle, _lib.dp(lo), _lib.dp(hi), C.c_uint64(int(seed)),
+            int(row0), int(n), _lib.dp(pars) if return_pars else None, _lib.dp(lnpost)))
+        return (pars, lnpost) if return_pars else lnpost
 
     def fit_mcmc(self, nwalkers=200, nburn=100, niter=200, p0=None, seed=0, thin=1, a=2.0):
         """emcee-style fit on the device (the reference's ``fit_mcmc_old``, starmodel.py:889-972: burn-in, reset,

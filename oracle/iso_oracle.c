@@ -533,6 +533,121 @@ void orc_mnest_prior(const double *bounds_lo, const double *bounds_hi, int32_t n
     for (i = 0; i < ndim; i++) cube[i] = (bounds_hi[i] - bounds_lo[i]) * cube[i] + bounds_lo[i];
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Ensemble sampler driver (test infrastructure / CPU baseline of BASELINE configs 3 and 4).
+ *
+ * The reference fits with emcee.EnsembleSampler(nwalkers, npars, self.lnpost) (starmodel.py:966, fit_mcmc_old
+ * :889-972); emcee itself is third-party and un-vendored (setup.py:60 "emcee>=2.0", unpinned).  What is restated here is
+ * its published algorithm, the stretch move of Goodman & Weare (2010) as emcee 2.x runs it: the ensemble is split in two
+ * halves updated in turn; walker k of the active half draws a partner c_j uniformly from the other half and
+ *     z = ((a - 1) u + 1)^2 / a,  q = c_j - z (c_j - x_k),  accepted iff  ln u' < (ndim - 1) ln z + lnpost(q) - lnpost(x_k).
+ * The uniforms come from Philox4x32-10 (Salmon et al. 2011) with the counters the product's device sampler uses
+ * (isochrones_b200/csrc/iso_stretch.cuh), so that a product chain can be replayed decision for decision.
+ * --------------------------------------------------------------------------------------------------------------- */
+static void orc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    int r;
+    for (r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+static double orc_u01(uint32_t hi, uint32_t lo)
+{
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* one proposal + accept test of walker k; returns 1 when accepted (pos / lnprob updated in place) */
+static int orc_stretch_one(const orc_model *m, double *pos, double *lnprob, int ndim, int nhalf, int half, int k, int chain,
+                           uint64_t gstep, uint64_t seed, double a)
+{
+    uint32_t r[4], r2[4];
+    uint64_t ctr = gstep * 2 + (uint64_t)half;
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32) ^ ((uint32_t)chain << 8);
+    uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
+    double q[8], u, u_acc, zr, z, lq, lnpdiff;
+    int j, d;
+    orc_philox4x32_10(c0, c1, (uint32_t)k, 0u, k0, k1, r);
+    orc_philox4x32_10(c0, c1, (uint32_t)k, 1u, k0, k1, r2);
+    u = orc_u01(r[0], r[1]);
+    j = (1 - half) * nhalf + (int)(r[2] % (uint32_t)nhalf);
+    u_acc = orc_u01(r2[0], r2[1]);
+    zr = (a - 1.0) * u + 1.0;
+    z = zr * zr / a;
+    for (d = 0; d < ndim; d++) {
+        double c = pos[j * ndim + d], x = pos[k * ndim + d];
+        q[d] = c - (c - x) * z;
+    }
+    lq = orc_lnpost(m, q);
+    lnpdiff = (ndim - 1) * log(z) + lq - lnprob[k];
+    if (lnpdiff > log(u_acc)) { /* NaN compares false: a NaN lnpost is a rejection */
+        for (d = 0; d < ndim; d++) pos[k * ndim + d] = q[d];
+        lnprob[k] = lq;
+        return 1;
+    }
+    return 0;
+}
+
+/* n_chains independent ensembles of n_walkers walkers advanced by n_steps; chain c samples models[c % n_models].
+ * pos [n_chains, n_walkers, ndim] and lnprob [n_chains, n_walkers] are updated in place (lnprob must hold lnpost of pos
+ * on entry); chain_out [n_steps, n_chains, n_walkers, ndim] / lnprob_out [n_steps, n_chains, n_walkers] may be NULL.
+ * Threads: over chains when there are several, else over the walkers of a half-step (they are independent). */
+void orc_stretch_move(const orc_model *const *models, int32_t n_models, int32_t n_chains, int32_t n_walkers, double *pos,
+                      double *lnprob, int64_t step0, int32_t n_steps, uint64_t seed, double a, double *chain_out,
+                      double *lnprob_out, int64_t *n_accepted, int32_t n_threads)
+{
+    int ndim = 4 + models[0]->n_stars, nhalf = n_walkers / 2;
+    int c;
+    (void)n_threads;
+    if (n_chains > 1) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+        for (c = 0; c < n_chains; c++) {
+            const orc_model *m = models[c % n_models];
+            double *p = pos + (size_t)c * n_walkers * ndim, *lp = lnprob + (size_t)c * n_walkers;
+            int64_t acc = 0;
+            int s, half, t;
+            for (s = 0; s < n_steps; s++) {
+                for (half = 0; half < 2; half++)
+                    for (t = 0; t < nhalf; t++)
+                        acc += orc_stretch_one(m, p, lp, ndim, nhalf, half, half * nhalf + t, c, (uint64_t)(step0 + s), seed, a);
+                if (chain_out)
+                    memcpy(chain_out + ((size_t)s * n_chains + c) * n_walkers * ndim, p, sizeof(double) * n_walkers * ndim);
+                if (lnprob_out) memcpy(lnprob_out + ((size_t)s * n_chains + c) * n_walkers, lp, sizeof(double) * n_walkers);
+            }
+            if (n_accepted) n_accepted[c] = acc;
+        }
+    } else {
+        const orc_model *m = models[0];
+        int64_t acc = 0;
+        int s, half, t;
+        for (s = 0; s < n_steps; s++) {
+            for (half = 0; half < 2; half++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : acc) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+                for (t = 0; t < nhalf; t++)
+                    acc += orc_stretch_one(m, pos, lnprob, ndim, nhalf, half, half * nhalf + t, 0, (uint64_t)(step0 + s), seed, a);
+            }
+            if (chain_out) memcpy(chain_out + (size_t)s * n_walkers * ndim, pos, sizeof(double) * n_walkers * ndim);
+            if (lnprob_out) memcpy(lnprob_out + (size_t)s * n_walkers, lnprob, sizeof(double) * n_walkers);
+        }
+        if (n_accepted) n_accepted[0] = acc;
+    }
+}
+
 int32_t orc_max_threads(void)
 {
 #ifdef _OPENMP

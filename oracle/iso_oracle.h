@@ -118,6 +118,11 @@ void orc_lnpost_batch(const orc_model *m, const double *pars, int64_t N, double 
 /* catalog mode: row i uses models[model_of_row[i]] */
 void orc_lnpost_catalog(const orc_model *const *models, const int32_t *model_of_row, const double *pars,
                         int64_t N, double *lnpost, int32_t n_threads);
+/* emcee's stretch move (the sampler the reference drives at starmodel.py:966) with the product's Philox counters:
+   n_chains ensembles advanced n_steps; see iso_oracle.c */
+void orc_stretch_move(const orc_model *const *models, int32_t n_models, int32_t n_chains, int32_t n_walkers, double *pos,
+                      double *lnprob, int64_t step0, int32_t n_steps, uint64_t seed, double a, double *chain_out,
+                      double *lnprob_out, int64_t *n_accepted, int32_t n_threads);
 void orc_mnest_prior(const double *bounds_lo, const double *bounds_hi, int32_t ndim, double *cube);
 int32_t orc_max_threads(void);
 

@@ -116,6 +116,10 @@ def lib():
         L.orc_lnpost_catalog.restype = None
         L.orc_lnpost_catalog.argtypes = [C.POINTER(C.POINTER(OrcModel)), c_int32_p, c_double_p, C.c_int64,
                                          c_double_p, C.c_int32]
+        L.orc_stretch_move.restype = None
+        L.orc_stretch_move.argtypes = [C.POINTER(C.POINTER(OrcModel)), C.c_int32, C.c_int32, C.c_int32, c_double_p,
+                                       c_double_p, C.c_int64, C.c_int32, C.c_uint64, C.c_double, c_double_p, c_double_p,
+                                       C.POINTER(C.c_int64), C.c_int32]
         L.orc_mnest_prior.restype = None
         L.orc_mnest_prior.argtypes = [c_double_p, c_double_p, C.c_int32, c_double_p]
         L.orc_max_threads.restype = C.c_int32
@@ -347,6 +351,31 @@ def lnpost_catalog(models, model_of_row, pars, n_threads=1):
     out = np.empty(n)
     lib().orc_lnpost_catalog(arr, _ip(mor), _dp(pars), n, _dp(out), n_threads)
     return out
+
+
+def stretch_move(models, p0, n_steps, seed, a=2.0, step0=0, n_threads=1, store=True):
+    """emcee's stretch move on the CPU with the product sampler's random stream (``orc_stretch_move``): ``models`` is one
+    ``StarModel`` (every chain samples it) or one per chain; ``p0`` is ``[n_walkers, ndim]`` or ``[n_chains, n_walkers,
+    ndim]``.  Returns ``(chain[n_steps, n_chains, n_walkers, ndim] or None, lnprob[...] or None, pos, lnprob_now,
+    n_accepted[n_chains])``."""
+    models = list(models) if isinstance(models, (list, tuple)) else [models]
+    pos = np.array(p0, dtype=np.float64)
+    if pos.ndim == 2:
+        pos = pos[None]
+    pos = np.ascontiguousarray(pos)
+    n_chains, n_walkers, ndim = pos.shape
+    assert ndim == models[0].ndim and len(models) in (1, n_chains)
+    lp = np.empty((n_chains, n_walkers))
+    for c in range(n_chains):
+        lp[c] = models[c % len(models)].lnpost_batch(pos[c], n_threads=n_threads)
+    arr = (C.POINTER(OrcModel) * len(models))(*[C.pointer(m.struct) for m in models])
+    chain = np.empty((n_steps, n_chains, n_walkers, ndim)) if store else None
+    lnp = np.empty((n_steps, n_chains, n_walkers)) if store else None
+    acc = np.zeros(n_chains, dtype=np.int64)
+    lib().orc_stretch_move(arr, len(models), n_chains, n_walkers, _dp(pos), _dp(lp), int(step0), int(n_steps),
+                           C.c_uint64(int(seed)), float(a), _dp(chain) if store else None, _dp(lnp) if store else None,
+                           acc.ctypes.data_as(C.POINTER(C.c_int64)), int(n_threads))
+    return chain, lnp, pos, lp, acc
 
 
 def max_threads():

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(L, name), "libisochrones_b200.so does not export %s" % name
     assert set(declared_symbols()) == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
-    assert L.iso_abi_version() == 2
+    assert L.iso_abi_version() == 3
 
 
 def test_struct_layout_matches_library():

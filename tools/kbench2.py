@@ -40,7 +40,8 @@ def main():
         ("scattered", mod, lambda s: bench.scattered_batch(n, seed=50 + s)),
         ("grid_wide", mod, lambda s: bench.grid_wide_batch(n, trk, seed=90 + s)),
     ]
-    if only is None or only & {"binary", "iso_single", "iso_prior"}:
+    extra = {"binary", "iso_single", "iso_prior", "catalog", "chains", "one_chain"}
+    if only is None or only & extra:
         iso = syn.make_iso_grid(columns=("Teff", "logg", "feh", "Mbol", "mass", "dm_deep", "nu_max", "delta_nu"))
         ici = ib.ichrone_from_arrays("iso", iso, bc, ctx=ctx)
         t2 = syn.default_truth("iso", n_stars=2)
@@ -88,7 +89,104 @@ def main():
                                                          int(np.isnan(out).sum())))
         for d in ptrs:
             ctx.dev_free(d)
+    if only is None or only & {"catalog", "chains", "one_chain"}:
+        parts += sampler_and_catalog(ctx, ici, single, t1, only, args)
     print("%-28s " % args.tag + " | ".join(parts), flush=True)
+
+
+def sampler_and_catalog(ctx, ic, single, truth1, only, args):
+    """bench.py's catalog (10 000 star models, 100 rows each through model_of_row) and on-device sampler workloads."""
+    import time
+
+    import pandas as pd
+
+    from isochrones_b200 import synthetic as syn
+    from isochrones_b200.catalog import StarCatalog
+    from isochrones_b200.sampler import DeviceEnsembleSampler
+
+    parts = []
+    if only is None or "catalog" in only:
+        n_stars, rows_per_star = 10_000, 100
+        rng = np.random.RandomState(8)
+        t = np.tile(truth1, (n_stars, 1))
+        t[:, 0] = rng.uniform(300.0, 900.0, n_stars)
+        t[:, 1] = rng.uniform(9.0, 9.9, n_stars)
+        t[:, 2] = rng.uniform(-0.5, 0.3, n_stars)
+        t[:, 3] = rng.uniform(50.0, 400.0, n_stars)
+        t[:, 4] = rng.uniform(0.0, 0.5, n_stars)
+        _, _, _, mg = ic.interp_mag([t[:, j] for j in range(5)], list(bench.BANDS))
+        table = {"parallax": 1000.0 / t[:, 3], "parallax_unc": np.full(n_stars, 0.1)}
+        for j, b in enumerate(bench.BANDS):
+            table[b + "_mag"] = mg[:, j]
+            table[b + "_mag_unc"] = np.full(n_stars, 0.02)
+        compiled = StarCatalog(pd.DataFrame(table), props=["parallax"]).compile(ic)
+        mor = np.repeat(np.arange(n_stars, dtype=np.int32), rows_per_star)
+        pars = np.repeat(t, rows_per_star, axis=0)
+        pars *= 1 + 0.002 * rng.standard_normal(pars.shape)
+        perm0 = np.random.RandomState(9).permutation(len(pars))
+        # the same catalog with the stars spread over the whole populated isochrone grid (what a real catalog does)
+        tw = t.copy()
+        tw[:, 0] = rng.uniform(210.0, 1400.0, n_stars)
+        tw[:, 1] = rng.uniform(7.5, 10.1, n_stars)
+        tw[:, 2] = rng.uniform(-3.5, 0.45, n_stars)
+        _, _, _, mgw = ic.interp_mag([tw[:, j] for j in range(5)], list(bench.BANDS))
+        bad = ~np.isfinite(mgw).all(axis=1)
+        tw[bad], mgw[bad] = t[bad], mg[bad]
+        tablew = {"parallax": 1000.0 / tw[:, 3], "parallax_unc": np.full(n_stars, 0.1)}
+        for j, b in enumerate(bench.BANDS):
+            tablew[b + "_mag"] = mgw[:, j]
+            tablew[b + "_mag_unc"] = np.full(n_stars, 0.02)
+        compiled_w = StarCatalog(pd.DataFrame(tablew), props=["parallax"]).compile(ic)
+        parsw = np.repeat(tw, rows_per_star, axis=0)
+        parsw *= 1 + 0.002 * rng.standard_normal(parsw.shape)
+        permw = np.random.RandomState(10).permutation(len(parsw))
+        cases = (("catalog", compiled, pars, mor), ("catalog_shuffled", compiled, pars[perm0], mor[perm0]),
+                 ("catalog_wide", compiled_w, parsw, mor), ("catalog_wide_shuffled", compiled_w, parsw[permw], mor[permw]))
+        for tag, compiled, pp, mm in cases:
+            pp, mm = np.ascontiguousarray(pp), np.ascontiguousarray(mm)
+            n_rows = len(pp)
+            d_p, d_m, d_o = ctx.dev_alloc(pp.nbytes), ctx.dev_alloc(mm.nbytes), ctx.dev_alloc(n_rows * 8)
+            ctx.h2d(d_p, pp)
+            ctx.h2d(d_m, mm)
+            for _ in range(3):
+                compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m)
+            ctx.sync()
+            ctx.timer_start()
+            for _ in range(args.steps):
+                compiled.lnpost_device(d_p, n_rows, d_o, d_model_of_row=d_m)
+            ms = ctx.timer_stop() / args.steps
+            res = np.empty(n_rows)
+            ctx.d2h(res, d_o)
+            fin = np.isfinite(res)
+            parts.append("%s %.4f ms %.2fe9/s [%d %.9e]" % (tag, ms, n_rows / ms / 1e6, int(fin.sum()), float(res[fin].sum())))
+            for d in (d_p, d_m, d_o):
+                ctx.dev_free(d)
+    nw = 256
+    if only is None or "one_chain" in only:
+        p0 = syn.posterior_like_batch("iso", nw, truth1, seed=4)
+        smp = DeviceEnsembleSampler(single.compiled, nw, p0, seed=4)
+        smp.run_mcmc(50, store=False)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            smp.run_mcmc(2000, store=False)
+            ts.append(time.perf_counter() - t0)
+        parts.append("one_chain 256x2000 min %.2f med %.2f max %.2f ms" % (1e3 * min(ts), 1e3 * sorted(ts)[2], 1e3 * max(ts)))
+        smp.close()
+    if only is None or "chains" in only:
+        n_chains, steps_c = 1184, 100
+        p0c = np.stack([syn.posterior_like_batch("iso", nw, truth1, seed=1000 + c) for c in range(8)])
+        p0c = np.ascontiguousarray(np.tile(p0c, (n_chains // 8, 1, 1)))
+        smc = DeviceEnsembleSampler(single.compiled, nw, p0c, seed=5, n_chains=n_chains)
+        smc.run_mcmc(10, store=False)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            smc.run_mcmc(steps_c, store=False)
+            ts.append(time.perf_counter() - t0)
+        parts.append("chains 1184x256x100 %.2f ms %.2fe9/s" % (1e3 * min(ts), n_chains * nw * steps_c / min(ts) / 1e9))
+        smc.close()
+    return parts
 
 
 if __name__ == "__main__":
