@@ -10,7 +10,10 @@
 // half-step publishes the half-step number in this rank's slot of every rank's flag array (system-scope release), and
 // the NEXT half-step kernel starts by waiting (bounded, ISO_E_TIMEOUT) until every rank has published the previous one.
 // That wait also orders the roles: a rank starts overwriting the half its peers were reading only after every peer has
-// finished reading it.
+// finished reading it.  Two more orderings follow from the same flags: a run starts with a token of its own (the peers
+// may not store into a copy its host may still be reading between runs), and a kept (thinned) ensemble is copied out in
+// two parts — the half that the step's second half-step does not move by that kernel itself before it publishes (the
+// peers overwrite it right after), the moved half after the step's completion wait.
 //
 // The proposal is iso_stretch.cuh's — the same code, the same Philox counters (half-step, walker) as the one-GPU
 // persistent sampler — so the chain does not depend on the number of ranks: world-size-N and single-GPU runs agree bit
@@ -57,6 +60,10 @@ struct IsoEnsembleParams {
     double a;
     int n_walkers, half, first, count;     // this rank moves walkers [half * nhalf + first, .. + count)
     int n_peers, rank;
+    // kept sample (second half-step of a thinned step only): the kernel itself copies the COMPLEMENTARY half — final
+    // since the previous half-step, and overwritten by the peers as soon as this rank publishes — before it publishes;
+    // the moved half is copied out after the step's completion wait (iso_ensemble_run)
+    double *keep_pos, *keep_lp;            // [n_walkers, ndim], [n_walkers] of this kept sample, or NULL
 };
 
 __device__ __forceinline__ unsigned long long iso_ens_globaltimer()
@@ -95,6 +102,14 @@ __global__ void __launch_bounds__(256, 2) iso_ensemble_half_kernel(const __grid_
     const int nhalf = P.n_walkers >> 1;
     const double *pos = P.state;
     const double *lp = P.state + (size_t)P.n_walkers * NDIMP;
+    if (P.keep_pos) {
+        const int w0 = (1 - P.half) * nhalf;   // first walker of the complementary half
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhalf * NDIMP; i += gridDim.x * blockDim.x)
+            P.keep_pos[(size_t)w0 * NDIMP + i] = pos[(size_t)w0 * NDIMP + i];
+        if (P.keep_lp)
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhalf; i += gridDim.x * blockDim.x)
+                P.keep_lp[w0 + i] = lp[w0 + i];
+    }
     unsigned long long n_acc = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += gridDim.x * blockDim.x) {
         const int k = P.half * nhalf + P.first + i;
@@ -153,6 +168,14 @@ __global__ void iso_ensemble_wait_kernel(const unsigned long long *own_flags, in
     }
     __syncthreads();
     __threadfence_system();
+}
+
+// start-of-run token: a rank's copy may be read by its host (iso_ensemble_state) between runs, so the peers may only
+// start storing into it again once this rank has entered the next run
+__global__ void iso_ensemble_signal_kernel(IsoEnsembleParams P)
+{
+    const int r = threadIdx.x;
+    if (r < P.n_peers) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.peer_flags[r] + P.rank), "l"(P.publish) : "memory");
 }
 
 static void ensemble_free(iso_ensemble *e)
@@ -350,6 +373,13 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;   // a rank without walkers in the half still waits and publishes
     cudaError_t ce = cudaSuccess;
+    P.keep_pos = P.keep_lp = nullptr;
+    P.half = 0;
+    P.gstep = 0;
+    P.wait_for = 0;
+    P.publish = ++e->published;   // the start-of-run token
+    iso_ensemble_signal_kernel<<<1, 32, 0, ctx->stream>>>(P);
+    ctx->launches++;
 #define ISO_ELAUNCH(NS, PROF, TRK)                                                                                       \
     do {                                                                                                                 \
         if (smem > 48 * 1024)                                                                                            \
@@ -359,10 +389,14 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     } while (0)
     for (int s = 0; s < n_steps && ce == cudaSuccess; s++) {
         P.gstep = (unsigned long long)(e->step + s);
+        const bool keep = (s + 1) % thin == 0 && (d_chain || d_lp);
+        const long long kept = (s + 1) / thin - 1;
         for (int half = 0; half < 2 && ce == cudaSuccess; half++) {
             P.half = half;
             P.wait_for = e->published;
             P.publish = ++e->published;
+            P.keep_pos = (keep && half == 1 && d_chain) ? d_chain + (size_t)kept * pos_n : nullptr;
+            P.keep_lp = (keep && half == 1 && d_lp) ? d_lp + (size_t)kept * e->n_walkers : nullptr;
             switch (e->models->n_stars) {
             case 1:
                 if (track) {
@@ -384,16 +418,17 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
             }
             ctx->launches++;
         }
-        if (ce == cudaSuccess && (s + 1) % thin == 0 && (d_chain || d_lp)) {
-            // the kept ensemble is complete once every rank has published this step's second half
-            const long long keep = (s + 1) / thin - 1;
+        if (ce == cudaSuccess && keep) {
+            // the first half of the kept ensemble was copied by the kernel above; the half it moved is complete once
+            // every rank has published this half-step, and stays untouched until this rank publishes the next one
+            const size_t h1 = (size_t)nhalf;
             iso_ensemble_wait_kernel<<<1, 32, 0, ctx->stream>>>(e->d_flags, e->nranks, e->published, e->timeout_ns, e->d_err);
             ctx->launches++;
             if (d_chain)
-                ce = cudaMemcpyAsync(d_chain + (size_t)keep * pos_n, e->d_state, pos_n * sizeof(double), cudaMemcpyDeviceToDevice,
-                                     ctx->stream);
+                ce = cudaMemcpyAsync(d_chain + (size_t)kept * pos_n + h1 * e->ndim, e->d_state + h1 * e->ndim,
+                                     h1 * e->ndim * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
             if (ce == cudaSuccess && d_lp)
-                ce = cudaMemcpyAsync(d_lp + (size_t)keep * e->n_walkers, e->d_state + pos_n, (size_t)e->n_walkers * sizeof(double),
+                ce = cudaMemcpyAsync(d_lp + (size_t)kept * e->n_walkers + h1, e->d_state + pos_n + h1, h1 * sizeof(double),
                                      cudaMemcpyDeviceToDevice, ctx->stream);
         }
     }

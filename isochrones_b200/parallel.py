@@ -186,11 +186,32 @@ class FileRendezvous(object):
             pass
 
 
+def preload_nccl():
+    """Make ``libnccl.so.2`` resolvable for the library's ``dlopen``: the system one if present, else the copy the
+    ``nvidia-nccl`` wheel ships (found through the import system, without importing torch)."""
+    try:
+        C.CDLL("libnccl.so.2", mode=C.RTLD_GLOBAL)
+        return "libnccl.so.2"
+    except OSError:
+        pass
+    import importlib.util
+
+    spec = importlib.util.find_spec("nvidia.nccl")
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            return cand
+    return None
+
+
 class NcclGather(object):
-    """All-gather of float64 device buffers across the ranks' contexts (``iso_nccl_init`` / ``iso_allgather_f64``)."""
+    """All-gather of float64 device buffers across the ranks' contexts (``iso_nccl_init`` / ``iso_allgather_f64``).
+    ``exchange(payload) -> rank 0's payload`` ships the 128-byte unique id (``FileRendezvous.broadcast``, ..)."""
 
     def __init__(self, ctx, rank, world, exchange):
         self.ctx, self.rank, self.world = ctx, rank, world
+        preload_nccl()
         buf = C.create_string_buffer(128)
         if rank == 0:
             ctx.check(_lib.lib().iso_nccl_unique_id(buf))
