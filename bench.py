@@ -639,10 +639,12 @@ def binary_batch(n, t2, seed):
     return p
 
 
-def catalog_fit(ctx, ic, rk, comm, args, n_stars=10_000, nw=64, n_steps=1600, with_cpu=True):
-    """BASELINE configs[3] at its stated size, as a FIT: 10 000 independent star models x >= 1e5 lnpost each (64 walkers
-    x 1600 steps = 102 400), stars sharded over the ranks (1250 per GPU at N = 8), one on-device chain per star
-    (iso_sampler_*, catalog mode), walkers and samples never leave HBM; the per-star posterior means / spreads come from
+def catalog_fit(ctx, ic, rk, comm, args, n_stars=10_000, nw=256, n_steps=400, thin=10, with_cpu=True):
+    """BASELINE configs[3] at its stated size, as a FIT: 10 000 independent star models x >= 1e5 lnpost each (256 walkers
+    x 400 steps = 102 400; the reference's own recipe is 300 walkers x 300 steps, starmodel.py:889), stars sharded over
+    the ranks (1250 per GPU at N = 8), one on-device chain per star (iso_sampler_*, catalog mode; more chains than
+    resident CTAs are worked through in 16-step segments from a queue), walkers and samples never leave HBM (the running
+    moments take every 10th ensemble); the per-star posterior means / spreads come from
     the kernel's running moments and are all-gathered (ncclAllGather) so that every rank holds the catalog's summary."""
     from isochrones_b200 import parallel
     from isochrones_b200.catalog import StarCatalog
@@ -662,13 +664,13 @@ def catalog_fit(ctx, ic, rk, comm, args, n_stars=10_000, nw=64, n_steps=1600, wi
     mor = np.repeat(np.arange(b - a, dtype=np.int32), nw)
     bad = ~np.isfinite(compiled.lnpost(flat, model_of_row=mor))
     flat[bad] = np.repeat(truths, nw, axis=0)[bad]
-    smp = DeviceEnsembleSampler(compiled, nw, p0, seed=5, n_chains=b - a)
+    smp = DeviceEnsembleSampler(compiled, nw, p0, seed=5, n_chains=b - a, moments=True)
     smp.run_mcmc(20, store=False)          # burn-in + warm-up of the launch path
     smp.reset()
     ctx.sync()
     rk.barrier()
     ctx.timer_start()
-    smp.run_mcmc(n_steps, store=False)
+    smp.run_mcmc(n_steps, thin=thin, store=False)
     ms = rk.max(ctx.timer_stop())
     rk.barrier()
     mean, std, cnt = smp.moments()
@@ -710,11 +712,12 @@ def catalog_fit(ctx, ic, rk, comm, args, n_stars=10_000, nw=64, n_steps=1600, wi
         "summary_gather_ms": ms_gather, "summary_gather_bytes_per_rank": sh.pad * n_mom * 8, "scaling": "strong",
         "pcie_bytes_per_eval": 0,
         "config": "configs[3] at size: %d star models (iso grid, VJHK + parallax, truths spread over the whole populated "
-                  "grid) x %d walkers x %d steps = %d lnpost per star, stars sharded over %d GPU(s), one persistent CTA per "
-                  "star, all steps in one launch; summaries = running moments gathered with ncclAllGather"
+                  "grid) x %d walkers x %d steps = %d lnpost per star, stars sharded over %d GPU(s), one chain per star, all "
+                  "steps in one launch (resident CTAs claim 16-step segments of chains from a queue); summaries = running "
+                  "moments gathered with ncclAllGather"
                   % (n_stars, nw, n_steps, nw * n_steps, rk.world)}
     if with_cpu and rk.rank == 0:
-        out["cpu"] = cpu_catalog_fit(cat, ic, truths, n_sample=min(96, b - a), nw=nw, n_steps=200, seed=5)
+        out["cpu"] = cpu_catalog_fit(cat, ic, truths, n_sample=min(96, b - a), nw=nw, n_steps=50, seed=5)
         out["vs_cpu"] = out["value"] / out["cpu"]["value"]
     return out
 
@@ -1090,6 +1093,8 @@ def main():
         run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; this run prints ONE JSON line there
     rk = Ranks()
     rank, world, local_rank = rk.rank, rk.world, rk.local_rank
     from isochrones_b200 import _lib, parallel, synthetic as syn

@@ -266,6 +266,9 @@ int iso_sampler_state(iso_ctx *ctx, iso_sampler *s, double *h_pos, double *h_lnp
  * running moments; the walkers stay where they are.  The burn-in / production split of the reference's
  * fit_mcmc_old (starmodel.py:955-969). */
 int iso_sampler_reset(iso_ctx *ctx, iso_sampler *s);
+/* enable != 0: every kept (thinned) ensemble of the following runs is added to the running sums below (off by default:
+ * with thin = 1 the accumulation costs ~10 % of a step). */
+int iso_sampler_set_moments(iso_ctx *ctx, iso_sampler *s, int enable);
 /* Running sums over every kept (thinned) ensemble since the last reset, per chain: [n_chains, 2 ndim + 1] =
  * (sum x_d, sum x_d^2, number of samples).  h_moments (host copy; synchronises) and d_moments (the device array itself,
  * e.g. as the send buffer of iso_allgather_f64 in a multi-GPU catalog fit) may each be NULL. */

@@ -115,6 +115,7 @@ SIGNATURES = {
     "iso_sampler_run": (C.c_int, [_VP, _VP, C.c_int, C.c_int, c_double_p, c_double_p]),
     "iso_sampler_state": (C.c_int, [_VP, _VP, c_double_p, c_double_p, c_int64_p, c_int64_p]),
     "iso_sampler_reset": (C.c_int, [_VP, _VP]),
+    "iso_sampler_set_moments": (C.c_int, [_VP, _VP, C.c_int]),
     "iso_sampler_moments": (C.c_int, [_VP, _VP, c_double_p, C.POINTER(_VP)]),
     "iso_sampler_destroy": (C.c_int, [_VP, _VP]),
     "iso_ensemble_create": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, c_double_p, C.c_uint64, C.c_double, C.c_int, C.c_int,

@@ -17,9 +17,10 @@ from . import _lib
 
 
 class DeviceEnsembleSampler(object):
-    def __init__(self, compiled, n_walkers, p0, seed=0, a=2.0, n_chains=1):
+    def __init__(self, compiled, n_walkers, p0, seed=0, a=2.0, n_chains=1, moments=False):
         """``compiled``: ``CompiledModel`` (``BasicStarModel.compiled`` or ``compile_catalog(...)[0]``);
-        ``p0``: initial walkers ``[n_walkers, ndim]`` or ``[n_chains, n_walkers, ndim]``."""
+        ``p0``: initial walkers ``[n_walkers, ndim]`` or ``[n_chains, n_walkers, ndim]``; ``moments``: keep running
+        sums of every kept (thinned) ensemble on the device (``moments()``)."""
         self.compiled = compiled
         self.ctx = compiled.ctx
         self.ndim = compiled.ndim
@@ -39,6 +40,8 @@ class DeviceEnsembleSampler(object):
         self._chains = []
         self._lnprobs = []
         self.n_steps = 0
+        if moments:
+            self.ctx.check(_lib.lib().iso_sampler_set_moments(self.ctx.handle, self.handle, 1))
 
     def run_mcmc(self, n_steps, thin=1, store=True):
         """Advance every chain by ``n_steps`` ensemble steps (one launch).  Returns ``(pos, lnprob)`` like emcee."""

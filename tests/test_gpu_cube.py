@@ -110,7 +110,7 @@ def test_sampler_reset_and_running_moments(world):
     good = pars[np.isfinite(gl["lp_%s_lnpost" % name])]
     n_chains, nw = 3, 32
     p0 = np.stack([good[c * nw:(c + 1) * nw] for c in range(n_chains)])
-    smp = DeviceEnsembleSampler(mod.compiled, nw, p0, seed=9, n_chains=n_chains)
+    smp = DeviceEnsembleSampler(mod.compiled, nw, p0, seed=9, n_chains=n_chains, moments=True)
     smp.run_mcmc(30, store=False)                                # burn-in
     _, _, acc_burn, prop_burn = smp.state()
     assert prop_burn == 30 * nw

@@ -123,3 +123,27 @@ def test_catalog_chains(setup):
         again = DeviceEnsembleSampler(compiled, n_walkers, p0, seed=5, n_chains=6)
         again.run_mcmc(40)
         assert np.array_equal(again.chains[:, s], chain)
+
+
+def test_work_queue_of_multi_wave_runs_matches_the_oracle_chains(setup):
+    """More chains than resident CTAs: the kernel works through (chain, 16-step segment) items from a queue.  The chains
+    must not depend on the schedule — each one is replayed by the oracle's C driver with the same stream."""
+    from isochrones_b200.sampler import DeviceEnsembleSampler
+    from oracle import oracle
+
+    mod, om, truth, syn = setup["track"]
+    n_chains, nw, n_steps, seed = 2900, 8, 40, 99          # 2900 one-warp CTAs on 148 SMs x 16 resident: 1.22 waves
+    base = syn.posterior_like_batch("track", 4000, truth, n_eep=171, seed=21)
+    base = base[np.isfinite(om.lnpost_batch(base))][:nw * 50]
+    p0 = np.ascontiguousarray(np.stack([base[(c % 50) * nw:(c % 50 + 1) * nw] for c in range(n_chains)]))
+    smp = DeviceEnsembleSampler(mod.compiled, nw, p0, seed=seed, n_chains=n_chains, moments=True)
+    smp.run_mcmc(n_steps, thin=8)
+    pos, lnp, acc, prop = smp.state()
+    mean, std, cnt = smp.moments()
+    chain, _, opos, olp, oacc = oracle.stretch_move(om, p0, n_steps, seed, n_threads=8)
+    assert np.array_equal(pos, opos)                       # identical decisions -> identical ensembles, all 2600 chains
+    assert np.allclose(lnp, olp, rtol=1e-12, atol=1e-8) and np.array_equal(acc, oacc)
+    assert np.array_equal(smp.chains, chain[7::8])         # kept (thinned) ensembles land in the right slots
+    assert (cnt == (n_steps // 8) * nw).all()
+    assert np.allclose(mean, chain[7::8].mean(axis=(0, 2)), rtol=1e-11, atol=1e-11)
+    smp.close()
