@@ -63,14 +63,18 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+KERNEL_SOURCES = ("iso_common.cuh", "iso_prior.cuh", "iso_philox.cuh", "iso_lnpost_row.cuh", "iso_lnpost_kernel.cuh",
+                  "iso_lnpost_k1.cu")
+
+
 def kernel_source_hash():
-    """SHA-256 over the CUDA sources: ties an ncu capture (profiles/traffic.json) to the kernels being timed."""
+    """SHA-256 over the sources the fused single-star lnpost kernel is compiled from: ties an ncu capture
+    (profiles/traffic.json) to the kernel being timed."""
     d = os.path.join(ROOT, "isochrones_b200", "csrc")
     h = hashlib.sha256()
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 

@@ -90,6 +90,15 @@ static int convert_model(iso_ctx *ctx, const iso_model &s, IsoModelDev &d)
     else
         def = def && other.self.kind == ISO_PRIOR_FLATLOG && iso_prior_is_chabrier_like(d.eep_orig);
     d.profile_default = def ? 1 : 0;
+    d.eep_lnc[0] = d.eep_lnc[1] = 0.0;
+    if (def && !d.eep_replaces_age) {
+        // pdf(mass) / eep_norm = comp_i._pdf(mass) / comp_i._norm / norms[i] / _norm / eep_norm; the x-independent part:
+        //   LogNormal (priors.py:272-275): 1 / (sqrt(2 pi) s scale);   PowerLaw (priors.py:469-471): (1 + alpha) / (hi^(1+alpha) - lo^(1+alpha))
+        const iso_prior &op = d.eep_orig;
+        const double common = op.inv_norm * d.eep_inv_norm;
+        d.eep_lnc[0] = log(op.comp[0].k[1] * op.comp[0].k[2] * op.inv_norms[0] * common);
+        d.eep_lnc[1] = log(op.comp[1].k[2] * op.inv_norms[1] * common);
+    }
     return ISO_OK;
 }
 

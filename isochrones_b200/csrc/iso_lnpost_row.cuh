@@ -35,6 +35,9 @@ struct IsoModelDev {
     IsoGaussDev mag[ISO_MAX_BANDS];   // indexed by BC-pack column
     IsoGaussDev plax, nu_max, delta_nu;
     double eep_lo, eep_hi, eep_norm, eep_inv_norm;
+    // default profile on isochrone grids (orig_prior = Chabrier-like BrokenPrior[LogNormal, PowerLaw] of the mass): log of
+    // every x-independent factor of orig_prior(mass) / eep_norm per component, so that ln(pdf dm/dEEP) is a sum of logs
+    double eep_lnc[2];
     iso_prior eep_orig, mass, age, feh, distance, AV;
     int profile_default;   // 1: the priors match ISO_PROFILE_DEFAULT
     int pad2_;
@@ -365,9 +368,27 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                     lnp_eep[k] = neg_inf;
                 else
                     lnp_eep[k] = fma(age, op.k[0], iso_log_or_neginf(op.k[2] * v[ISO_MP_DERIV] * m.eep_inv_norm));
+            } else if (DEF) {
+                // orig_prior = Chabrier-like broken prior of the mass, called as Prior.__call__ (bounds test, then
+                // components[i](x) / norms[i] / _norm, priors.py:35-36, 54-59, 205-207).  The density is positive wherever it
+                // is not cut to zero, so log(pdf * deriv / norm) = ln pdf + log(deriv): one log(mass) serves both components
+                // (walkers around the 1 Msun break diverge inside a warp) and no exp / pow is evaluated.  0 -> -inf,
+                // negative / NaN deriv -> NaN, as in `np.log(pdf) if pdf else -np.inf`.
+                const iso_prior &op = m.eep_orig;
+                const double mass = v[ISO_MP_ORIG];
+                const bool upper = mass != mass || op.breakpoints[0] <= mass;   // np.digitize: NaN -> last component
+                const iso_prior_leaf &c = upper ? op.comp[1] : op.comp[0];
+                if (((op.self.flags & ISO_PF_HAS_BOUNDS) && iso_outside(mass, op.self.lo, op.self.hi)) ||
+                    ((c.flags & ISO_PF_HAS_BOUNDS) && iso_outside(mass, c.lo, c.hi))) {
+                    lnp_eep[k] = neg_inf;
+                } else {
+                    const double lnm = log(mass);
+                    const double ly = lnm - op.comp[0].a[0], t = ly * op.comp[0].k[3];      // LogNormal: y = mass / scale
+                    const double ln_pdf = upper ? fma(op.comp[1].a[0], lnm, m.eep_lnc[1]) : m.eep_lnc[0] - ly - 0.5 * (t * t);
+                    lnp_eep[k] = ln_pdf + iso_log_or_neginf(v[ISO_MP_DERIV]);
+                }
             } else {
-                double pdf = DEF ? iso_broken2_call<ISO_PRIOR_LOGNORMAL, ISO_PRIOR_POWERLAW>(m.eep_orig, v[ISO_MP_ORIG])
-                                 : iso_prior_call_dyn(&m.eep_orig, v[ISO_MP_ORIG]);
+                double pdf = iso_prior_call_dyn(&m.eep_orig, v[ISO_MP_ORIG]);
                 lnp_eep[k] = iso_log_or_neginf(pdf * v[ISO_MP_DERIV] * m.eep_inv_norm);
             }
             if (!SEQ) Mbol[k] = v[ISO_MP_MBOL];

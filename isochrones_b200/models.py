@@ -352,14 +352,14 @@ class ModelGridInterpolator(object):
         if names:
             table.update(zip(names, self.interp_value([m, e, f], names).T))
         if bands:
-            mags = self.interp_mag([m, e, f, d, av], bands)[3]
+            mags = np.atleast_2d(self.interp_mag([m, e, f, d, av], bands)[3])     # a single star comes back 1-D
             table.update(("{}_mag".format(b), mags[:, j]) for j, b in enumerate(bands))
         if not (return_df or return_dict):
             out = np.column_stack(list(table.values())) if table else np.empty((len(m), 0))
             return out[0] if shape == () else out
         table.update(distance=d, AV=av, initial_feh=f, requested_age=a)
         if all_As and bands:
-            clear = self.interp_mag([m, e, f, d, np.zeros_like(av)], bands)[3]
+            clear = np.atleast_2d(self.interp_mag([m, e, f, d, np.zeros_like(av)], bands)[3])
             table.update(("A_{}".format(b), table["{}_mag".format(b)] - clear[:, j]) for j, b in enumerate(bands))
         if return_dict:
             return {k: (v[0] if shape == () else v) for k, v in table.items()}

@@ -69,6 +69,26 @@ class CompiledModel(object):
             return float(h_out[0]), float(h_out[1]), float(h_out[2])
         return float(h_out[0])
 
+    def cube_one(self, cube, lo, hi):
+        """MultiNest's per-live-point call pair in ONE launch: the unit-cube point ``cube`` (any indexable of ``ndim``
+        numbers) is mapped through the box ``[lo, hi]`` and evaluated (``iso_mnest_lnpost_batch`` on a page-locked row:
+        the library's small-call path).  Returns ``(mapped parameters as a list, lnpost)``."""
+        one = self._one
+        buf = getattr(one, "cube", None)
+        if buf is None:
+            if self.n_models != 1:
+                raise ValueError("unit-cube rows need a single compiled model")
+            h_row, h_out = self.ctx.pinned_empty((1, self.ndim)), self.ctx.pinned_empty((1,))
+            buf = one.cube = (h_row, h_out, _lib.dp(h_row), _lib.dp(h_out), _lib.lib().iso_mnest_lnpost_batch, self.ctx.handle,
+                              self.model_pack.handle, self.bc_pack.handle)
+        h_row, h_out, p_row, p_out, fn, ctxh, mph, bph = buf
+        for i in range(self.ndim):
+            h_row[0, i] = cube[i]
+        rc = fn(ctxh, mph, bph, self.handle, _lib.dp(lo), _lib.dp(hi), p_row, 1, p_out, None, None)
+        if rc:
+            self.ctx.check(rc)
+        return h_row[0].tolist(), float(h_out[0])
+
     def lnpost(self, pars, parts=False, model_of_row=None, out=None):
         """``pars[N, ndim]`` -> ``lnpost[N]`` (and ``lnprior[N]``, ``lnlike[N]`` when ``parts``)."""
         pars = np.asarray(pars)
@@ -235,6 +255,7 @@ class BasicStarModel(object):
         return self._bounds[prop]
 
     def set_bounds(self, **kwargs):
+        self._mnest_last = None
         for k, v in kwargs.items():
             if len(v) != 2:
                 raise ValueError("Must provide (min, max)")
@@ -243,6 +264,7 @@ class BasicStarModel(object):
         self._compiled = None
 
     def set_prior(self, **kwargs):
+        self._mnest_last = None
         for prop, prior in kwargs.items():
             self._priors[prop] = prior
             self._bounds[prop] = prior.bounds
@@ -320,26 +342,43 @@ class BasicStarModel(object):
         return self.compiled.lnpost_one(p)
 
     def mnest_prior(self, cube, ndim=None, nparams=None):
-        """Unit cube -> parameter box, in place (starmodel.py:1637-1640); ``cube`` may be ``[ndim]`` or ``[N, ndim]``."""
+        """Unit cube -> parameter box, in place (starmodel.py:1637-1640); ``cube`` may be ``[ndim]`` — a list, an array
+        or the ctypes ``double *`` pymultinest hands over — or a float64 array ``[N, ndim]``.
+
+        MultiNest calls ``mnest_prior(cube)`` and then ``mnest_loglike(cube)`` for every live point.  The single-point
+        form therefore runs the fused cube kernel (mapping + lnpost in one launch) and remembers the lnpost of the
+        mapped point; the ``mnest_loglike`` that follows finds its cube unchanged and returns it without a second
+        launch."""
         lo, hi = self._box()
-        arr = np.asarray(cube)
-        direct = isinstance(cube, np.ndarray) and arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
-        work = arr if direct else np.ascontiguousarray([cube[i] for i in range(len(lo))], dtype=np.float64)
-        n = work.size // len(lo)
-        ctx = self.ic.ctx
-        ctx.check(_lib.lib().iso_mnest_prior(ctx.handle, _lib.dp(lo), _lib.dp(hi), len(lo), _lib.dp(work), n))
-        if not direct:      # e.g. the ctypes double* pymultinest hands over
-            for i in range(len(lo)):
-                cube[i] = work[i]
+        if isinstance(cube, np.ndarray) and cube.ndim == 2:
+            if cube.dtype != np.float64 or not cube.flags["C_CONTIGUOUS"]:
+                raise ValueError("a batch of cube points must be a C-contiguous float64 array (it is mapped in place)")
+            ctx = self.ic.ctx
+            ctx.check(_lib.lib().iso_mnest_prior(ctx.handle, _lib.dp(lo), _lib.dp(hi), len(lo), _lib.dp(cube), cube.shape[0]))
+            return
+        mapped, lnpost = self.compiled.cube_one(cube, lo, hi)
+        for i, v in enumerate(mapped):
+            cube[i] = v
+        self._mnest_last = (mapped, lnpost)
 
     def mnest_loglike(self, cube, ndim=None, nparams=None):
-        n = self.n_params
-        return self.lnpost([cube[i] for i in range(n)])
+        vals = [cube[i] for i in range(self.n_params)]
+        last = getattr(self, "_mnest_last", None)
+        if last is not None and last[0] == vals:      # the point mnest_prior has just mapped (and evaluated)
+            return last[1]
+        return self.lnpost(vals)
 
     def _box(self):
-        lo = np.array([self.bounds(par)[0] for par in self.param_names], dtype=np.float64)
-        hi = np.array([self.bounds(par)[1] for par in self.param_names], dtype=np.float64)
-        return lo, hi
+        """``(lo, hi)`` of every parameter; cached on the compiled model, which is dropped whenever a bound changes."""
+        c = self.compiled
+        box = getattr(c, "box", None)
+        if box is None:
+            lo = np.array([self.bounds(par)[0] for par in self.param_names], dtype=np.float64)
+            hi = np.array([self.bounds(par)[1] for par in self.param_names], dtype=np.float64)
+            if self._compiled is not c:       # bounds() of an unset parameter re-compiles: take the current model
+                c = self.compiled
+            box = c.box = (lo, hi)
+        return box
 
     def mnest_lnpost_batch(self, cube, parts=False):
         """``mnest_prior`` + ``mnest_loglike`` (starmodel.py:1637-1645) of a whole set of live points in ONE launch:
