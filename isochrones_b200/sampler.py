@@ -43,8 +43,9 @@ class DeviceEnsembleSampler(object):
         if moments:
             self.ctx.check(_lib.lib().iso_sampler_set_moments(self.ctx.handle, self.handle, 1))
 
-    def run_mcmc(self, n_steps, thin=1, store=True):
-        """Advance every chain by ``n_steps`` ensemble steps (one launch).  Returns ``(pos, lnprob)`` like emcee."""
+    def run_mcmc(self, n_steps, thin=1, store=True, fetch=True):
+        """Advance every chain by ``n_steps`` ensemble steps (one launch).  Returns ``(pos, lnprob)`` like emcee;
+        ``fetch=False`` leaves the ensemble on the device (nothing is copied to the host) and returns ``None``."""
         n_keep = n_steps // thin
         chain = np.empty((n_keep, self.n_chains, self.n_walkers, self.ndim)) if store else None
         lnp = np.empty((n_keep, self.n_chains, self.n_walkers)) if store else None
@@ -55,7 +56,7 @@ class DeviceEnsembleSampler(object):
             self._chains.append(chain)
             self._lnprobs.append(lnp)
         self.n_steps += n_steps
-        return self.state()[:2]
+        return self.state()[:2] if fetch else None
 
     def reset(self):
         """Forget the stored samples, the acceptance counters and the running moments (walker positions are kept), as
@@ -172,9 +173,10 @@ class ShardedEnsembleSampler(object):
     def set_timeout(self, seconds):
         self.ctx.check(_lib.lib().iso_ensemble_set_timeout(self.ctx.handle, self.handle, float(seconds)))
 
-    def run_mcmc(self, n_steps, thin=1, store=True):
+    def run_mcmc(self, n_steps, thin=1, store=True, fetch=True):
         """Advance the ensemble by ``n_steps`` steps (every rank calls this with the same arguments); ``store`` keeps
-        the thinned chain on THIS rank.  Returns ``(pos[n_walkers, ndim], lnprob[n_walkers])``."""
+        the thinned chain on THIS rank.  Returns ``(pos[n_walkers, ndim], lnprob[n_walkers])``, or ``None`` with
+        ``fetch=False`` (the ensemble stays on the device)."""
         n_keep = n_steps // thin
         chain = np.empty((n_keep, self.n_walkers, self.ndim)) if store else None
         lnp = np.empty((n_keep, self.n_walkers)) if store else None
@@ -184,7 +186,7 @@ class ShardedEnsembleSampler(object):
             self._chains.append(chain)
             self._lnprobs.append(lnp)
         self.n_steps += n_steps
-        return self.state()[:2]
+        return self.state()[:2] if fetch else None
 
     def state(self):
         """``(pos, lnprob, proposals accepted by this rank, proposals per ensemble)``."""

@@ -165,11 +165,11 @@ def sampler_and_catalog(ctx, ic, single, truth1, only, args):
     if only is None or "one_chain" in only:
         p0 = syn.posterior_like_batch("iso", nw, truth1, seed=4)
         smp = DeviceEnsembleSampler(single.compiled, nw, p0, seed=4)
-        smp.run_mcmc(50, store=False)
+        smp.run_mcmc(50, store=False, fetch=False)
         ts = []
         for _ in range(5):
             t0 = time.perf_counter()
-            smp.run_mcmc(2000, store=False)
+            smp.run_mcmc(2000, store=False, fetch=False)
             ts.append(time.perf_counter() - t0)
         parts.append("one_chain 256x2000 min %.2f med %.2f max %.2f ms" % (1e3 * min(ts), 1e3 * sorted(ts)[2], 1e3 * max(ts)))
         smp.close()
@@ -178,11 +178,11 @@ def sampler_and_catalog(ctx, ic, single, truth1, only, args):
         p0c = np.stack([syn.posterior_like_batch("iso", nw, truth1, seed=1000 + c) for c in range(8)])
         p0c = np.ascontiguousarray(np.tile(p0c, (n_chains // 8, 1, 1)))
         smc = DeviceEnsembleSampler(single.compiled, nw, p0c, seed=5, n_chains=n_chains)
-        smc.run_mcmc(10, store=False)
+        smc.run_mcmc(10, store=False, fetch=False)
         ts = []
         for _ in range(3):
             t0 = time.perf_counter()
-            smc.run_mcmc(steps_c, store=False)
+            smc.run_mcmc(steps_c, store=False, fetch=False)
             ts.append(time.perf_counter() - t0)
         parts.append("chains 1184x256x100 %.2f ms %.2fe9/s" % (1e3 * min(ts), n_chains * nw * steps_c / min(ts) / 1e9))
         smc.close()
