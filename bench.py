@@ -854,6 +854,19 @@ def extra_workloads(ctx, bc, args, peak, rk):
     if rk.world == 1:
         out["catalog_10k_stars_fit"] = catalog_fit(ctx, ic, rk, None, args)
         out["sharded_ensemble_1M_walkers"] = sharded_ensemble(ctx, single, t1, rk, args)
+        # the reference's DEFAULT fit: nested sampling, 1000 live points, evidence tolerance 0.5 (starmodel.py:667-671,
+        # 717-802; published: "about 14 minutes on my laptop" for a binary, docs/multiple.ipynb) over the full prior box
+        t0 = time.perf_counter()
+        res = single.fit_nested(n_live_points=1000, seed=1, max_batches=4000)
+        dt = time.perf_counter() - t0
+        out["nested_fit_1000_live_points"] = {
+            "value": res.n_evals / dt, "unit": UNIT, "seconds": dt, "n_evals": res.n_evals, "n_iter": res.n_iter,
+            "logZ": res.logZ, "logZ_err": res.logZ_err, "information_nats": res.information, "efficiency": res.efficiency,
+            "finite_fraction_of_prior_box": res.finite_fraction, "converged": res.converged,
+            "posterior_mean": [float(v) for v in res.mean()], "posterior_std": [float(v) for v in res.std()],
+            "config": "BasicStarModel.fit_nested on the isochrone-grid single star over the full prior box: host-driven nested "
+                      "sampling (single bounding ellipsoid), every batch of 8192 candidate live points = one "
+                      "iso_mnest_lnpost_batch launch (cube -> parameters -> lnpost)"}
     return out
 
 

@@ -431,6 +431,16 @@ class BasicStarModel(object):
         self._sampler = sampler
         return sampler
 
+    def fit_nested(self, n_live_points=1000, evidence_tolerance=0.5, seed=0, **kwargs):
+        """Nested sampling of this model — the reference's default ``fit()`` path (``fit_multinest``,
+        starmodel.py:717-802: ``pymultinest.run(self.mnest_loglike, self.mnest_prior, ...)`` with
+        ``n_live_points=1000``, ``evidence_tolerance=0.5``) with every batch of likelihood evaluations as one GPU launch
+        (:mod:`isochrones_b200.nested`).  Returns a ``NestedResult`` (``logZ``, weighted ``samples`` ...)."""
+        from .nested import nested_sample
+
+        self._nested = nested_sample(self, n_live=n_live_points, dlogz=evidence_tolerance, seed=seed, **kwargs)
+        return self._nested
+
     def sample_from_prior(self, n, values=False, require_valid=True):
         """Prior draws, re-drawn until ``lnpost`` is finite (starmodel.py:1716-1748); host RNG, batched validity check."""
         import pandas as pd
