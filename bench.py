@@ -362,6 +362,46 @@ def cpu_baseline(trk, bc, ic_host_model, seed, budget_s=12.0):
                       "kernels + priors), OpenMP over %d threads, %.1f s" % (n, threads, dt)}
 
 
+def reference_as_shipped(budget_calls=4000):
+    """The UNMODIFIED reference (pure Python + numba) on this box's host cores: its sources travel as an archive under
+    oracle/_ref/ (oracle/build_ref.py, git-ignored) and are timed by oracle/time_reference.py in a subprocess — the scalar
+    `BasicStarModel.lnpost(p)` loop on one core, and the reference's own batch recipe (a process pool over all cores)."""
+    import shutil
+    import tarfile
+    import tempfile
+
+    archive = os.path.join(ROOT, "oracle", "_ref", "isochrones_reference.tar.gz")
+    if not os.path.exists(archive):
+        return {"unavailable": "oracle/_ref/isochrones_reference.tar.gz not built (run __graft_entry__.build() where /root/reference exists)"}
+    tmp = tempfile.mkdtemp(prefix="iso_ref_")
+    try:
+        with tarfile.open(archive) as tar:
+            tar.extractall(tmp)
+        env = dict(os.environ, NUMBA_CACHE_DIR=os.path.join(tmp, "numba_cache"))
+        env.pop("OMP_NUM_THREADS", None)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference.py"), "--root", tmp, "--pool", "--json",
+                            "--calls", str(budget_calls)], capture_output=True, text=True, timeout=600, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": "time_reference.py failed: %s" % (r.stderr[-300:] or r.stdout[-300:])}
+        t = json.loads(lines[-1])
+        out = {"kind": "reference", "unit": UNIT, "value": t["lnpost_scalar"]["evals_per_s"], "cores": 1,
+               "us_per_call": t["lnpost_scalar"]["us_per_call"],
+               "sample": "%d calls of the unmodified reference's BasicStarModel.lnpost(p) (pure Python + numba), posterior-like "
+                         "rows of the bench workload, one core" % t["lnpost_scalar"]["calls"],
+               "interp_mag_points_per_s": t["interp_mag_arrays"]["points_per_s"],
+               "interp_value_points_per_s": t["interp_value_arrays"]["points_per_s"]}
+        if "lnpost_scalar_pool" in t:
+            out["pool"] = {"value": t["lnpost_scalar_pool"]["evals_per_s"], "cores": t["lnpost_scalar_pool"]["processes"],
+                           "sample": "%d calls over multiprocessing.Pool(%d): the reference's own batch recipe"
+                                     % (t["lnpost_scalar_pool"]["calls"], t["lnpost_scalar_pool"]["processes"])}
+        return out
+    except Exception as e:
+        return {"unavailable": repr(e)[:300]}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def cpu_chain(model, p0, n_steps, seed):
     """configs[2] on the host cores: the oracle's lnpost driven by the same stretch move (oracle.stretch_move; the
     walkers of a half-step fan out over all threads).  Returns evals/s and the wall time."""
@@ -1228,6 +1268,7 @@ def main():
         line["consistency_failures"] = failed
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(trk, bc, mod, seed=900)
+        line["cpu_baseline"]["reference_as_shipped"] = reference_as_shipped()
     print(json.dumps(line), flush=True)
     if failed:
         sys.exit(3)
