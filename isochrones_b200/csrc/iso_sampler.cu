@@ -13,6 +13,7 @@
 // fill the GPU.  Randomness is counter-based (Philox4x32-10 keyed by seed, counter = step / half / walker / chain),
 // so a run is reproducible and independent of scheduling; tests replay the same stream on the host.
 #include <math.h>
+#include <stdlib.h>
 
 #include "iso_lnpost_row.cuh"
 #include "iso_stretch.cuh"
