@@ -142,72 +142,74 @@ class BasicStarModel(object):
 
     def __init__(self, ic, eep_bounds=None, name="", directory=".", N=1, maxAV=None, max_distance=None,
                  halo_fraction=None, ra=None, dec=None, obs=None, use_emcee=False, **kwargs):
-        self._ic = ic
-        self.eep_bounds = eep_bounds if eep_bounds is not None else self.ic.eep_bounds
-        self.name = str(name)
-        self.use_emcee = use_emcee
-        self.ra = ra
-        self.dec = dec
-        self.obs = None
-
         if N not in (1, 2, 3):
             raise ValueError("N must be 1, 2 or 3")
-        if N > 1 and ic.eep_replaces == "age":
-            raise ValueError("Can only fit mulitple stars with IsochroneInterpolator!")
-        self.N = N
-        # position of every shared parameter in a row: the N leading slots are the per-star parameters
-        # (mass for the single star of a track model, EEPs otherwise); see param_names
-        for slot, par in enumerate(ic.param_names):
-            if par not in ("eep",):
-                setattr(self, par + "_index", slot if slot == 0 else slot + N - 1)
+        self._ic, self.N = ic, N
+        if N > 1 and self.ic.eep_replaces == "age":
+            raise ValueError("binary / triple fits need the isochrone-grid interpolator (per-star EEPs, one shared age)")
+        self.name, self._directory = str(name), str(directory)
+        self.use_emcee, self.ra, self.dec, self.obs = use_emcee, ra, dec, None
+        self.eep_bounds = self.ic.eep_bounds if eep_bounds is None else eep_bounds
+        self._samples = self._derived_samples = None
+        self._bands = self._spec_props = self._props = self._param_names = self._compiled = None
 
-        # observations: (value, uncertainty) pairs; NaN pairs count as "not observed" and anything that is not a
-        # pair is ignored (the reference logs a warning, starmodel.py:1423-1432)
-        self.kwargs = {}
-        for key, pair in kwargs.items():
-            if key == "use_emcee":
-                continue
-            try:
-                value, sigma = pair
-            except TypeError:
-                continue
-            if not (np.isnan(value) or np.isnan(sigma)):
-                self.kwargs[key] = (np.float64(value), np.float64(sigma))
-
-        self._bands = None
-        self._spec_props = None
-        self._props = None
-        self._param_names = None
-        self._compiled = None
-
-        self._priors = {"mass": ChabrierPrior(), "feh": FehPrior(), "age": AgePrior(),
-                        "distance": DistancePrior(), "AV": AVPrior()}
-        self._priors["eep"] = EEP_prior(self.ic, self._priors[self.ic.eep_replaces], bounds=eep_bounds)
-        for pr in self._priors.values():
-            pr._owner = self.ic      # stand-alone evaluations (prior.lnpdf(x)) run on the model's own GPU context
-        self._bounds = {"mass": None, "feh": None, "age": None, "distance": DistancePrior().bounds,
-                        "AV": AVPrior().bounds, "eep": self._priors["eep"].bounds}
-        # Reset bounds to match IC bounds (starmodel.py:1458-1460)
-        for par in ["mass", "feh", "age"]:
-            self.bounds(par)
-        if maxAV is not None:
-            self.set_bounds(AV=(0, maxAV))
-        if max_distance is not None:
-            self.set_bounds(distance=(0, max_distance))
-        else:
-            if "parallax" in kwargs:
-                value, unc = kwargs["parallax"]
-                if value > 0:
-                    self.set_bounds(distance=(0, 1.0 / value * 2000))
-                elif value < 0:
-                    self.set_bounds(distance=(0, 1.0 / np.abs(unc) * 2000))
+        self._number_row_slots()
+        self.kwargs = self._measurements(kwargs)
+        self._install_default_priors(eep_bounds)
+        self._clip_box(maxAV, max_distance)
         if halo_fraction is not None:
+            # as in the reference (starmodel.py:1478-1479) the two-population [Fe/H] prior keeps ITS OWN default support:
+            # it is installed after the box was clipped to the grid
             self._priors["feh"] = FehPrior(halo_fraction=halo_fraction)
             self._priors["feh"]._owner = self.ic
 
-        self._directory = str(directory)
-        self._samples = None
-        self._derived_samples = None
+    def _number_row_slots(self):
+        """``<par>_index`` attributes (starmodel.py:1403-1421): where each shared parameter sits in a row.  The row starts
+        with the per-star slots — N EEPs, or the one mass of a track model — so a shared parameter at position ``j`` of the
+        interpolator's own list lands at ``j + N - 1``."""
+        for j, par in enumerate(self.ic.param_names):
+            if par != "eep":
+                setattr(self, par + "_index", j + (self.N - 1 if j else 0))
+
+    @staticmethod
+    def _measurements(given):
+        """Keyword observations -> ``{name: (value, sigma)}`` in float64.  Anything that does not unpack as a pair is
+        dropped, and so is a pair with a NaN in it: "not observed" (starmodel.py:1423-1432, which warns instead)."""
+        kept = {}
+        for key, item in given.items():
+            try:
+                value, sigma = item
+            except TypeError:
+                continue
+            pair = (np.float64(value), np.float64(sigma))
+            if key != "use_emcee" and not np.isnan(pair).any():
+                kept[key] = pair
+        return kept
+
+    def _install_default_priors(self, eep_bounds):
+        """The reference's default prior set (starmodel.py:1441-1460) and the sampling box that goes with it: mass, [Fe/H]
+        and age take the model grid's own limits, distance and A_V their prior's support, EEP the requested bounds."""
+        shared = {"mass": ChabrierPrior(), "feh": FehPrior(), "age": AgePrior(), "distance": DistancePrior(), "AV": AVPrior()}
+        shared["eep"] = EEP_prior(self.ic, shared[self.ic.eep_replaces], bounds=eep_bounds)
+        self._priors, self._bounds = shared, {}
+        for par, pr in shared.items():
+            pr._owner = self.ic          # stand-alone evaluations (prior.lnpdf(x)) run on the model's own GPU context
+            self._bounds[par] = None if par in self._grid_limited else pr.bounds
+        for par in self._grid_limited:
+            self.bounds(par)
+
+    def _clip_box(self, maxAV, max_distance):
+        """Optional tightening of the box (starmodel.py:1462-1476): explicit caps first; without a distance cap a
+        measured parallax bounds the distance at twice the parallax distance (of the value, or of |sigma| if negative)."""
+        if maxAV is not None:
+            self.set_bounds(AV=(0, maxAV))
+        plx = self.kwargs.get("parallax")
+        if max_distance is not None:
+            self.set_bounds(distance=(0, max_distance))
+        elif plx is not None and plx[0] != 0:
+            self.set_bounds(distance=(0, 1.0 / (plx[0] if plx[0] > 0 else np.abs(plx[1])) * 2000))
+
+    _grid_limited = ("mass", "feh", "age")
 
     # ---- reference attribute surface ---------------------------------------------------------------------
     @property
@@ -241,18 +243,17 @@ class BasicStarModel(object):
         return len(self.param_names)
 
     def bounds(self, prop):
-        if prop in ["eep_0", "eep_1", "eep_2"]:
-            prop = "eep"
-        if self._bounds[prop] is not None:
-            return self._bounds[prop]
-        elif prop in ("mass", "feh", "age"):
-            lo, hi = self.ic.model_grid.get_limits(prop)
-            self._bounds[prop] = (lo, hi)
-            self._priors[prop].bounds = (lo, hi)
+        """(lo, hi) of one row parameter (starmodel.py:1538-1552); ``eep_k`` share the ``eep`` entry.  The grid-limited
+        parameters resolve lazily to the model grid's limits, which also become the support of their prior."""
+        key = "eep" if prop in ("eep_0", "eep_1", "eep_2") else prop
+        box = self._bounds.get(key)
+        if box is None:
+            if key not in self._grid_limited:
+                raise ValueError("Unknown property {}".format(prop))
+            box = tuple(self.ic.model_grid.get_limits(key))
+            self._bounds[key] = self._priors[key].bounds = box
             self._compiled = None
-        else:
-            raise ValueError("Unknown property {}".format(prop))
-        return self._bounds[prop]
+        return box
 
     def set_bounds(self, **kwargs):
         self._mnest_last = None
