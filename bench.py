@@ -766,10 +766,11 @@ def catalog_fit(ctx, ic, rk, comm, args, n_stars=10_000, nw=256, n_steps=400, th
     return out
 
 
-def sharded_ensemble(ctx, single, t1, rk, args, n_walkers=1 << 20, n_steps=10):
+def sharded_ensemble(ctx, single, t1, rk, args, n_walkers=1 << 20, n_steps=50):
     """ONE ensemble of 2^20 walkers sharded over the ranks (iso_ensemble_*): per half-step a rank evaluates its block of
-    the active half and its kernel stores the accepted walkers into every rank's copy over NVLink (the consumer of the
-    fused peer exchange).  Checked: all ranks end with identical copies, and identical to a single-rank run."""
+    the active half, and each proposal gathers its partner walker from the HBM of the rank that owns it over NVLink peer
+    mappings (the multi-GPU consumer of the fused peer exchange); a run ends with one replication of every rank's blocks.
+    Checked: all ranks end with identical copies, and identical to a single-rank run."""
     from isochrones_b200 import synthetic as syn
     from isochrones_b200.sampler import ShardedEnsembleSampler
 
@@ -779,11 +780,20 @@ def sharded_ensemble(ctx, single, t1, rk, args, n_walkers=1 << 20, n_steps=10):
     ens = ShardedEnsembleSampler(single.compiled, n_walkers, p0, seed=13, rank=rk.rank, world=rk.world,
                                  allgather_bytes=rk.allgather_bytes)
     ens.run_mcmc(2, store=False, fetch=False)
-    ctx.sync()
-    rk.barrier()
-    ctx.timer_start()
-    ens.run_mcmc(n_steps, store=False, fetch=False)
-    ms = rk.max(ctx.timer_stop())
+    n_short = 10
+
+    def timed_run(n):
+        # the ranks are aligned on the DEVICE: a one-step run ends with every rank waiting for every rank's replication,
+        # so all ranks leave it within microseconds (a file barrier would leave them milliseconds apart, and the first
+        # half-step of the timed run would wait for the slowest rank to arrive)
+        rk.barrier()
+        ens.run_mcmc(1, store=False, fetch=False)
+        ctx.timer_start()
+        ens.run_mcmc(n, store=False, fetch=False)
+        return rk.max(ctx.timer_stop())
+
+    ms_short = timed_run(n_short)
+    ms = timed_run(n_steps)
     pos, lnp, acc, prop = ens.state()
     digest = hashlib.sha256(pos.tobytes() + lnp.tobytes()).hexdigest()
     same_copies = len(set(rk.allgather_bytes(digest.encode()))) == 1
@@ -791,20 +801,26 @@ def sharded_ensemble(ctx, single, t1, rk, args, n_walkers=1 << 20, n_steps=10):
     rk.barrier()
     ens.close()
     same_single = None
+    total_steps = 2 + (1 + n_short) + (1 + n_steps)
     if rk.rank == 0:
         one = ShardedEnsembleSampler(single.compiled, n_walkers, p0, seed=13)
-        one.run_mcmc(2 + n_steps, store=False, fetch=False)
+        one.run_mcmc(total_steps, store=False, fetch=False)
         p1, l1, _, _ = one.state()
         same_single = hashlib.sha256(p1.tobytes() + l1.tobytes()).hexdigest() == digest
         one.close()
     rk.barrier()
     evals = n_walkers * n_steps
+    marginal = (ms - ms_short) / (2 * (n_steps - n_short))
     return {"value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_half_step": ms / (2 * n_steps), "walkers": n_walkers,
-            "steps": n_steps, "acceptance_fraction": accepted / float(n_walkers * (n_steps + 2)),
+            "steps": n_steps, "ms_per_half_step_marginal": marginal,
+            "run_overhead_ms": ms_short - 2 * n_short * marginal,
+            "acceptance_fraction": accepted / float(n_walkers * total_steps),
             "copies_identical_across_ranks": same_copies, "identical_to_single_rank_run": same_single, "scaling": "strong",
-            "config": "one ensemble of %d walkers on the iso grid sharded over %d rank(s); accepted walkers (48 B) stored "
-                      "into every rank's copy by the evaluation kernel over NVLink peer mappings, flag exchange per "
-                      "half-step, no collective launch" % (n_walkers, rk.world)}
+            "config": "one ensemble of %d walkers on the iso grid sharded over %d rank(s), %d steps in one run; each "
+                      "proposal gathers its partner walker (40 B) from the owning rank's HBM over NVLink peer mappings inside "
+                      "the evaluation kernel, flag exchange per half-step, no collective launch; the run ends with one "
+                      "replication of every rank's blocks into every copy (inside the timed region: run_overhead_ms = "
+                      "launch + replication, from a 10-step run timed beside it)" % (n_walkers, rk.world, n_steps)}
 
 
 def extra_workloads(ctx, bc, args, peak, rk):

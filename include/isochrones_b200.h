@@ -306,9 +306,11 @@ int iso_peer_check(iso_ctx *ctx, iso_peer_group *group);
 int iso_peer_destroy(iso_ctx *ctx, iso_peer_group *group);
 
 /* ------------------------------------------------------------------------------------------------
- * ONE ensemble sharded over the GPUs of a node: every rank holds the whole ensemble, moves its block
- * of the active half per half-step and stores accepted walkers (position + lnpost) into every rank's copy through
- * CUDA-IPC peer mappings inside the evaluation kernel; no collective launch.  Same stretch move and Philox stream as
+ * ONE ensemble sharded over the GPUs of a node: every rank owns a block of each half, moves its block
+ * of the active half per half-step, and each proposal gathers its partner walker from the owning rank's memory through
+ * CUDA-IPC peer mappings inside the evaluation kernel; no collective launch.  A run ends (and every kept step of a
+ * thinned chain is preceded) by one replication of all blocks, so every rank holds the whole ensemble between runs and
+ * iso_ensemble_state reads locally.  Same stretch move and Philox stream as
  * iso_sampler_*: the chain is independent of the number of ranks (bit for bit).  Setup as for iso_peer_*: create on
  * every rank with the same h_p0 / seed, export 128 bytes, all-gather them, connect.  Every rank must call
  * iso_ensemble_run with the same arguments; h_chain [n_steps / thin, n_walkers, ndim] and h_lnprob

@@ -111,7 +111,14 @@ struct IsoPeerTargets {
     unsigned *done;               // CTA arrival counter (own device memory, zero between launches)
     long long offset;             // this rank's block starts here in every receive buffer
     int n, rank;
+    // in-kernel completion wait (ISO_PEER_INKERNEL_WAIT): the last CTA, after publishing, waits for every rank's flag
+    const unsigned long long *own_flags;
+    unsigned long long timeout_ns;
+    unsigned *err;
 };
+#ifndef ISO_PEER_INKERNEL_WAIT
+#define ISO_PEER_INKERNEL_WAIT 1
+#endif
 struct iso_models;
 int iso_lnpost_launch_peers(iso_ctx *ctx, const iso_grid *model_pack, const iso_grid *bc_pack, const iso_models *models,
                             const int32_t *d_model_of_row, const double *d_pars, int64_t N, const IsoPeerTargets *peers);   // builds model_pack->d_pair if absent

@@ -2,18 +2,22 @@
 // stretch-move sampler, one all-gather of the accepted half-ensemble + their lnprob per half-step").
 //
 // The reference's samplers evaluate the walkers of a half-step one Python call at a time (emcee, starmodel.py:966) or
-// spread live points over MPI ranks (MultiNest, starmodel.py:755-797).  Here every rank (one process per GPU) holds the
-// WHOLE ensemble in its own HBM; in a half-step a rank proposes and evaluates only its block of the active half and
-// writes every ACCEPTED walker (position + lnpost) straight into the ensemble copy of every rank — plain stores through
-// CUDA-IPC peer mappings, carried by NVLink — so the exchange is fused into the evaluation kernel: no collective is
-// launched and nothing but accepted walkers travels.  Completion is the flag protocol of iso_peer.cu: the last CTA of a
-// half-step publishes the half-step number in this rank's slot of every rank's flag array (system-scope release), and
-// the NEXT half-step kernel starts by waiting (bounded, ISO_E_TIMEOUT) until every rank has published the previous one.
-// That wait also orders the roles: a rank starts overwriting the half its peers were reading only after every peer has
-// finished reading it.  Two more orderings follow from the same flags: a run starts with a token of its own (the peers
-// may not store into a copy its host may still be reading between runs), and a kept (thinned) ensemble is copied out in
-// two parts — the half that the step's second half-step does not move by that kernel itself before it publishes (the
-// peers overwrite it right after), the moved half after the step's completion wait.
+// spread live points over MPI ranks (MultiNest, starmodel.py:755-797).  Here every rank (one process per GPU) OWNS a
+// contiguous block of each half of the ensemble; in a half-step a rank proposes and evaluates its block of the active
+// half, and every proposal GATHERS its partner walker c_j — drawn uniformly from the complementary half — straight from
+// the HBM of the rank that owns it: plain loads through CUDA-IPC peer mappings, carried by NVLink.  The exchange is
+// fused into the evaluation kernel — no collective is launched, and only the 8 * ndim bytes a proposal actually needs
+// travel (a first version pushed every accepted walker into every rank's copy instead: 7 x 48 B of scattered 8-byte
+// remote stores per accepted walker made the half-step SLOWER with more GPUs — 0.131 ms at N = 8 against 0.098 ms on
+// one GPU for 2^20 walkers, profiles/README.md).  Accepted walkers are written to the owner's own memory only.
+// Completion is the flag protocol of iso_peer.cu: the last CTA of a half-step publishes the half-step number in this
+// rank's slot of every rank's flag array (system-scope release), and the NEXT half-step kernel starts by waiting
+// (bounded, ISO_E_TIMEOUT) until every rank has published the previous one.  That one wait orders both directions: the
+// partners a rank is about to read are final (their owners finished the previous half-step), and a rank starts
+// overwriting its block of a half only after every peer has finished reading it.  At the end of a run (and at every
+// kept step of a thinned chain) each rank pushes its two blocks into every peer's copy with coalesced stores
+// (iso_ensemble_share_kernel), so between runs every rank holds the whole ensemble: iso_ensemble_state reads locally.
+// A run starts with a token of its own: the peers may not store into a copy its host may still be reading.
 //
 // The proposal is iso_stretch.cuh's — the same code, the same Philox counters (half-step, walker) as the one-GPU
 // persistent sampler — so the chain does not depend on the number of ranks: world-size-N and single-GPU runs agree bit
@@ -50,7 +54,7 @@ struct IsoEnsembleParams {
     IsoRowGrids G;
     IsoModelDev model;
     double *state;                         // this rank's copy: pos [n_walkers, ndim], then lnpost [n_walkers]
-    double *peer_state[ISO_MAX_PEERS];
+    double *peer_state[ISO_MAX_PEERS];     // every rank's copy; rank r's blocks of it are the authoritative ones
     unsigned long long *peer_flags[ISO_MAX_PEERS];
     const unsigned long long *own_flags;
     unsigned long long wait_for, publish;  // half-step numbers: wait until every rank published `wait_for`, then publish
@@ -60,10 +64,7 @@ struct IsoEnsembleParams {
     double a;
     int n_walkers, half, first, count;     // this rank moves walkers [half * nhalf + first, .. + count)
     int n_peers, rank;
-    // kept sample (second half-step of a thinned step only): the kernel itself copies the COMPLEMENTARY half — final
-    // since the previous half-step, and overwritten by the peers as soon as this rank publishes — before it publishes;
-    // the moved half is copied out after the step's completion wait (iso_ensemble_run)
-    double *keep_pos, *keep_lp;            // [n_walkers, ndim], [n_walkers] of this kept sample, or NULL
+    int blk_base, blk_extra;               // block sizes of a half: ranks < blk_extra own blk_base + 1 walkers, the rest blk_base
 };
 
 __device__ __forceinline__ unsigned long long iso_ens_globaltimer()
@@ -73,15 +74,33 @@ __device__ __forceinline__ unsigned long long iso_ens_globaltimer()
     return t;
 }
 
-template <int NSTARS, int PROFILE, bool TRACK>
-__global__ void __launch_bounds__(256, 2) iso_ensemble_half_kernel(const __grid_constant__ IsoEnsembleParams P)
+// every thread's writes are ordered before its CTA's arrival (the CTA barrier, then the system-scope fences of warp 0:
+// cumulative, as in a grid-wide barrier); the last CTA to arrive publishes `publish` in this rank's slot on every rank
+__device__ __forceinline__ void iso_ensemble_publish(const IsoEnsembleParams &P)
 {
-    constexpr int NDIMP = NSTARS + 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
-    iso_stage_axis_tables(P.G, s_nodes);
-    // every rank has finished (and published) the previous half-step: its accepted walkers are in our copy, and nobody
-    // still reads the half we are about to overwrite
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned last = 0;
+        if (lane == 0) {
+            __threadfence_system();
+            last = atomicAdd(P.done, 1u) == gridDim.x - 1;
+            if (last) *P.done = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            // lane r serves rank r: one fence, then relaxed stores side by side (release stores one after the other would
+            // each wait for the previous one's NVLink round trip)
+            __threadfence_system();
+            if (lane < P.n_peers)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(P.peer_flags[lane] + P.rank), "l"(P.publish) : "memory");
+        }
+    }
+}
+
+// bounded wait (lanes 0 .. n_peers - 1 of every CTA) until every rank has published `wait_for`
+__device__ __forceinline__ void iso_ensemble_await(const IsoEnsembleParams &P)
+{
     if (P.wait_for > 0) {
         const int r = threadIdx.x;
         if (r < P.n_peers) {
@@ -99,53 +118,99 @@ __global__ void __launch_bounds__(256, 2) iso_ensemble_half_kernel(const __grid_
         }
         __syncthreads();
     }
-    const int nhalf = P.n_walkers >> 1;
-    const double *pos = P.state;
-    const double *lp = P.state + (size_t)P.n_walkers * NDIMP;
-    if (P.keep_pos) {
-        const int w0 = (1 - P.half) * nhalf;   // first walker of the complementary half
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhalf * NDIMP; i += gridDim.x * blockDim.x)
-            P.keep_pos[(size_t)w0 * NDIMP + i] = pos[(size_t)w0 * NDIMP + i];
-        if (P.keep_lp)
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nhalf; i += gridDim.x * blockDim.x)
-                P.keep_lp[w0 + i] = lp[w0 + i];
+}
+
+// A walker's position record (NDIMP doubles, 8-byte aligned) read as whole 32-byte sectors: one 256-bit load per sector
+// the record touches (2, for NDIMP = 7 sometimes 3) instead of NDIMP 8-byte loads — over NVLink every load instruction
+// of a scattered gather is a read request of its own.  L2-only (.cg): the record was written by another kernel, maybe on
+// another GPU.  Sectors lie inside the rank's state allocation (the lnpost array follows the positions).
+template <int NDIMP>
+__device__ __forceinline__ void iso_gather_record(const double *rec, double (&c)[NDIMP])
+{
+    const unsigned long long addr = (unsigned long long)rec;
+    const int sh = (int)((addr & 31ULL) >> 3);   // doubles between the sector boundary and the record
+    const double *base = reinterpret_cast<const double *>(addr & ~31ULL);
+    constexpr int NSEC = (NDIMP + 3 + 3) / 4;
+    double v[4 * NSEC];
+#pragma unroll
+    for (int sct = 0; sct < NSEC; sct++) {
+        v[4 * sct] = v[4 * sct + 1] = v[4 * sct + 2] = v[4 * sct + 3] = 0.0;
+        if (4 * sct < sh + NDIMP)
+            asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(v[4 * sct]), "=d"(v[4 * sct + 1]), "=d"(v[4 * sct + 2]), "=d"(v[4 * sct + 3])
+                         : "l"(base + 4 * sct));
     }
+#pragma unroll
+    for (int d = 0; d < NDIMP; d++) {
+        double t = v[d];
+        if (d + 1 < 4 * NSEC) t = sh == 1 ? v[d + 1] : t;
+        if (d + 2 < 4 * NSEC) t = sh == 2 ? v[d + 2] : t;
+        if (d + 3 < 4 * NSEC) t = sh == 3 ? v[d + 3] : t;
+        c[d] = t;
+    }
+}
+
+template <int NSTARS, int PROFILE, bool TRACK>
+__global__ void __launch_bounds__(256, 2) iso_ensemble_half_kernel(const __grid_constant__ IsoEnsembleParams P)
+{
+    constexpr int NDIMP = NSTARS + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *s_nodes = reinterpret_cast<double2 *>(smem_raw);
+    iso_stage_axis_tables(P.G, s_nodes);
+    // every rank has finished (and published) the previous half-step: the partners we are about to read are final, and
+    // nobody still reads the block we are about to overwrite
+    iso_ensemble_await(P);
+    const int nhalf = P.n_walkers >> 1;
+    const int other0 = (1 - P.half) * nhalf;
+    double *pos = P.state;
+    double *lp = P.state + (size_t)P.n_walkers * NDIMP;
+    const int big = P.blk_extra * (P.blk_base + 1);   // walkers of a half owned by the ranks with one walker more
     unsigned long long n_acc = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.count; i += gridDim.x * blockDim.x) {
         const int k = P.half * nhalf + P.first + i;
-        double q[NDIMP], z, u_acc;
-        iso_stretch_propose<NDIMP>(P.seed, P.gstep, P.half, 0, k, (1 - P.half) * nhalf, nhalf, P.a, pos, q, z, u_acc);
+        int j_rel;
+        double z, u_acc;
+        iso_stretch_draw(P.seed, P.gstep, P.half, 0, k, nhalf, P.a, j_rel, z, u_acc);
+        // the partner lives in the copy of the rank that owns block(j_rel) of the complementary half
+        const int owner = P.n_peers == 1 ? 0 : (j_rel < big ? j_rel / (P.blk_base + 1) : P.blk_extra + (j_rel - big) / P.blk_base);
+        const double *partner = P.peer_state[owner] + (size_t)(other0 + j_rel) * NDIMP;
+        double c[NDIMP], x[NDIMP], q[NDIMP];
+        iso_gather_record<NDIMP>(partner, c);
+#pragma unroll
+        for (int d = 0; d < NDIMP; d++) x[d] = pos[(size_t)k * NDIMP + d];
+        iso_stretch_point<NDIMP>(c, x, z, q);
         const IsoRowResult res = iso_lnpost_row<NSTARS, PROFILE, TRACK>(P.G, s_nodes, P.model, q, false, false);
         if (iso_stretch_accept<NDIMP>(z, u_acc, res.lnpost, lp[k])) {
 #pragma unroll
-            for (int r = 0; r < ISO_MAX_PEERS; r++) {
-                if (r < P.n_peers) {
-                    double *dst = P.peer_state[r];
-#pragma unroll
-                    for (int d = 0; d < NDIMP; d++) dst[(size_t)k * NDIMP + d] = q[d];
-                    dst[(size_t)P.n_walkers * NDIMP + k] = res.lnpost;
-                }
-            }
+            for (int d = 0; d < NDIMP; d++) pos[(size_t)k * NDIMP + d] = q[d];
+            lp[k] = res.lnpost;
             n_acc++;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
     if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(P.accepted, n_acc);
-    // every thread's peer stores are ordered before its arrival; the last CTA then publishes the half-step everywhere
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(P.done, 1u);
-        if (ticket == gridDim.x - 1) {
-            *P.done = 0;
-            __threadfence_system();
-#pragma unroll
-            for (int r = 0; r < ISO_MAX_PEERS; r++)
-                if (r < P.n_peers)
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.peer_flags[r] + P.rank), "l"(P.publish) : "memory");
+    iso_ensemble_publish(P);
+}
+
+// Replication: this rank's blocks of both halves (positions + lnpost) go into every peer's copy — contiguous runs,
+// coalesced stores — and the rank then publishes.  Launched once every rank has published the last half-step.
+__global__ void __launch_bounds__(256) iso_ensemble_share_kernel(const __grid_constant__ IsoEnsembleParams P, int ndim)
+{
+    iso_ensemble_await(P);
+    const int nhalf = P.n_walkers >> 1;
+    const double *lp = P.state + (size_t)P.n_walkers * ndim;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    for (int r = 0; r < P.n_peers; r++) {
+        if (r == P.rank) continue;
+        double *dst = P.peer_state[r];
+        for (int half = 0; half < 2; half++) {
+            const size_t k0 = (size_t)half * nhalf + P.first;
+            for (long long i = tid; i < (long long)P.count * ndim; i += nthr) dst[k0 * ndim + i] = P.state[k0 * ndim + i];
+            for (long long i = tid; i < P.count; i += nthr) dst[(size_t)P.n_walkers * ndim + k0 + i] = lp[k0 + i];
         }
     }
+    iso_ensemble_publish(P);
 }
 
 // final wait of a run (and the wait before a kept ensemble is copied out): same bounded spin as the kernel's prologue
@@ -356,6 +421,8 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     P.rank = e->rank;
     const int nhalf = e->n_walkers / 2;
     ensemble_block(nhalf, e->nranks, e->rank, &P.first, &P.count);
+    P.blk_base = nhalf / e->nranks;
+    P.blk_extra = nhalf % e->nranks;
     const long long n_keep = n_steps / thin;
     const size_t pos_n = (size_t)e->n_walkers * e->ndim;
     double *d_chain = nullptr, *d_lp = nullptr;
@@ -373,7 +440,6 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;   // a rank without walkers in the half still waits and publishes
     cudaError_t ce = cudaSuccess;
-    P.keep_pos = P.keep_lp = nullptr;
     P.half = 0;
     P.gstep = 0;
     P.wait_for = 0;
@@ -387,6 +453,20 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
                                       (int)smem);                                                                        \
         if (ce == cudaSuccess) iso_ensemble_half_kernel<NS, PROF, TRK><<<blocks, 256, smem, ctx->stream>>>(P);           \
     } while (0)
+    // replication + completion wait: every rank's blocks are in every copy when the wait kernel returns
+    int share_blocks = (int)(((long long)P.count * e->ndim + 255) / 256);
+    if (share_blocks > cap) share_blocks = cap;
+    if (share_blocks < 1) share_blocks = 1;
+    auto replicate = [&]() {
+        if (e->nranks > 1) {
+            P.wait_for = e->published;
+            P.publish = ++e->published;
+            iso_ensemble_share_kernel<<<share_blocks, 256, 0, ctx->stream>>>(P, e->ndim);
+            ctx->launches++;
+        }
+        iso_ensemble_wait_kernel<<<1, 32, 0, ctx->stream>>>(e->d_flags, e->nranks, e->published, e->timeout_ns, e->d_err);
+        ctx->launches++;
+    };
     for (int s = 0; s < n_steps && ce == cudaSuccess; s++) {
         P.gstep = (unsigned long long)(e->step + s);
         const bool keep = (s + 1) % thin == 0 && (d_chain || d_lp);
@@ -395,8 +475,6 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
             P.half = half;
             P.wait_for = e->published;
             P.publish = ++e->published;
-            P.keep_pos = (keep && half == 1 && d_chain) ? d_chain + (size_t)kept * pos_n : nullptr;
-            P.keep_lp = (keep && half == 1 && d_lp) ? d_lp + (size_t)kept * e->n_walkers : nullptr;
             switch (e->models->n_stars) {
             case 1:
                 if (track) {
@@ -419,23 +497,20 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
             ctx->launches++;
         }
         if (ce == cudaSuccess && keep) {
-            // the first half of the kept ensemble was copied by the kernel above; the half it moved is complete once
-            // every rank has published this half-step, and stays untouched until this rank publishes the next one
-            const size_t h1 = (size_t)nhalf;
-            iso_ensemble_wait_kernel<<<1, 32, 0, ctx->stream>>>(e->d_flags, e->nranks, e->published, e->timeout_ns, e->d_err);
-            ctx->launches++;
+            // a kept ensemble is whole only after a replication; the copy is then a plain device-to-device one (nobody
+            // writes into this rank's copy before this rank publishes its next half-step)
+            replicate();
             if (d_chain)
-                ce = cudaMemcpyAsync(d_chain + (size_t)kept * pos_n + h1 * e->ndim, e->d_state + h1 * e->ndim,
-                                     h1 * e->ndim * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+                ce = cudaMemcpyAsync(d_chain + (size_t)kept * pos_n, e->d_state, pos_n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     ctx->stream);
             if (ce == cudaSuccess && d_lp)
-                ce = cudaMemcpyAsync(d_lp + (size_t)kept * e->n_walkers + h1, e->d_state + pos_n + h1, h1 * sizeof(double),
+                ce = cudaMemcpyAsync(d_lp + (size_t)kept * e->n_walkers, e->d_state + pos_n, (size_t)e->n_walkers * sizeof(double),
                                      cudaMemcpyDeviceToDevice, ctx->stream);
         }
     }
 #undef ISO_ELAUNCH
     if (ce == cudaSuccess) {
-        iso_ensemble_wait_kernel<<<1, 32, 0, ctx->stream>>>(e->d_flags, e->nranks, e->published, e->timeout_ns, e->d_err);
-        ctx->launches++;
+        replicate();
         ce = cudaGetLastError();
     }
     if (ce == cudaSuccess && d_chain)

@@ -157,6 +157,9 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     a.peer_rank = 0;
     a.peer_step = 0;
     a.peer_done = nullptr;
+    a.peer_own_flags = nullptr;
+    a.peer_timeout_ns = 0;
+    a.peer_err = nullptr;
     a.claim = ctx->d_claim + ISO_CLAIM_STRIDE * (st == ctx->copy_stream[0] ? 1 : st == ctx->copy_stream[1] ? 2 : 0);
     for (int q = 0; q < ISO_MAX_PEERS; q++) {
         a.peer_out[q] = nullptr;
@@ -168,6 +171,9 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
         a.peer_rank = peers->rank;
         a.peer_step = peers->step;
         a.peer_done = peers->done;
+        a.peer_own_flags = peers->own_flags;
+        a.peer_timeout_ns = peers->timeout_ns;
+        a.peer_err = peers->err;
         for (int q = 0; q < peers->n; q++) {
             a.peer_out[q] = peers->out[q];
             a.peer_flags[q] = peers->flags[q];
@@ -178,7 +184,11 @@ static int lnpost_launch(iso_ctx *ctx, cudaStream_t st, const iso_grid *mp, cons
     f.profile_default = models->profile_default;
     f.track = models->track;
     f.peer = peers != nullptr;
-    f.seq = bp->dev.ncols == 4;   // multi-star models with at most four bands: the star-sequential kernels
+#ifndef ISO_SEQ_MAX_CHUNKS
+#define ISO_SEQ_MAX_CHUNKS 3
+#endif
+    // multi-star models: the star-sequential kernels for BC packs of 1..3 chunks of 4 bands, chunk-major beyond
+    f.seq = bp->dev.ncols / 4 <= ISO_SEQ_MAX_CHUNKS ? bp->dev.ncols / 4 : 0;
     f.cube = cube != nullptr;
     a.pars_out = nullptr;
     a.cube_seed = 0;

@@ -41,6 +41,9 @@ struct IsoLnpostArgs {
     unsigned long long *peer_flags[ISO_MAX_PEERS];
     unsigned long long peer_step;
     unsigned *peer_done;
+    const unsigned long long *peer_own_flags;   // ISO_PEER_INKERNEL_WAIT: this rank's flag array, timeout and error word
+    unsigned long long peer_timeout_ns;
+    unsigned *peer_err;
     unsigned long long *claim;   // dynamically scheduled kernels: [0] next unclaimed row beyond the first pass, [1] finished CTAs
     // CUBE kernels: rows are points of the unit hypercube, mapped to parameters by BasicStarModel.mnest_prior
     // (starmodel.py:1637-1640: cube[i] = (hi - lo) * cube[i] + lo, unfused) before they are evaluated
@@ -80,7 +83,7 @@ struct IsoLnpostParams {
 // with prefetch.global.L1 was slower than both everywhere (register pressure).
 // SEQ: star-sequential evaluation of multi-star models whose BC pack is a single 4-band chunk (iso_lnpost_row.cuh).
 // CUBE: rows are unit-cube points (MultiNest's live points; or drawn on the device when a.cube_rng is set).
-template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK, bool PEER = false, bool SEQ = false, bool CUBE = false,
+template <int NSTARS, bool CATALOG, int PROFILE, bool TRACK, bool PEER = false, int SEQ = 0, bool CUBE = false,
           int LAYOUT = ISO_MODEL_LAYOUT, int DYN = (NSTARS == 1 ? ISO_LNPOST_DYN_SINGLE : ISO_LNPOST_DYN_MULTI)>
 __global__ void __launch_bounds__(ISO_LNPOST_THREADS, NSTARS == 1 ? ISO_LNPOST_MIN_BLOCKS : ISO_LNPOST_MIN_BLOCKS_MULTI)
 iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
@@ -182,23 +185,52 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
         }
     }
     if (PEER) {
-        // every thread's peer stores are ordered before its arrival; the last CTA then raises the flags
-        __threadfence_system();
+        // The CTA barrier orders every thread's peer stores before the system-scope fences of warp 0 (causality is
+        // cumulative: the pattern of a grid-wide barrier).  The last CTA to arrive raises this rank's flag on every rank
+        // — lane q serves rank q: ONE fence, then relaxed stores that travel side by side (eight release stores in a
+        // row would each wait for the previous one's round trip over NVLink) — and, ISO_PEER_INKERNEL_WAIT, waits right
+        // here until every rank has raised its flag on ours, so the exchange step is one launch.
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(a.peer_done, 1u);
-            if (ticket == gridDim.x - 1) {
-                *a.peer_done = 0;
-                if (DYN != 0 && a.N > stride) {
-                    a.claim[0] = 0;
-                    a.claim[1] = 0;
-                }
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            unsigned last = 0;
+            if (lane == 0) {
                 __threadfence_system();
-#pragma unroll
-                for (int q = 0; q < ISO_MAX_PEERS; q++)
-                    if (q < a.n_peers)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[q] + a.peer_rank), "l"(a.peer_step)
-                                     : "memory");
+                last = atomicAdd(a.peer_done, 1u) == gridDim.x - 1;
+                if (last) {
+                    *a.peer_done = 0;
+                    if (DYN != 0 && a.N > stride) {
+                        a.claim[0] = 0;
+                        a.claim[1] = 0;
+                    }
+                }
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence_system();
+                if (lane < a.n_peers)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[lane] + a.peer_rank), "l"(a.peer_step)
+                                 : "memory");
+#if ISO_PEER_INKERNEL_WAIT
+                if (a.peer_own_flags && lane < a.n_peers) {
+                    unsigned long long t0, now, v;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    unsigned spins = 0;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.peer_own_flags + lane) : "memory");
+                        if (v >= a.peer_step) break;
+                        if ((++spins & 255u) == 0) {
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (now - t0 > a.peer_timeout_ns) {   // bounded: report the missing rank, do not hang the stream
+                                atomicCAS_system(a.peer_err, 0u, (unsigned)(lane + 1) | ((unsigned)a.peer_step << 8));
+                                break;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                __threadfence_system();
+#endif
             }
         }
     }
@@ -207,7 +239,8 @@ iso_lnpost_kernel(const __grid_constant__ IsoLnpostParams P)
 
 // what a launch needs to know to pick its instantiation
 struct IsoLnpostFlags {
-    bool catalog, profile_default, track, peer, seq, cube;
+    bool catalog, profile_default, track, peer, cube;
+    int seq;   // multi-star models: number of 4-band chunks of the BC pack (star-sequential kernels), else 0
 };
 
 // launch dispatch of one translation unit (NS stars)
@@ -235,10 +268,14 @@ static int iso_lnpost_dispatch(iso_ctx *ctx, cudaStream_t st, const IsoLnpostPar
 #define ISO_LAUNCH5(CAT, PROF, TRK, PEER)                                                                                \
     do {                                                                                                                 \
         if (f.cube && !CAT && !PEER) {                                                                                   \
-            if (NS > 1 && f.seq) ISO_LAUNCH7(false, PROF, TRK, false, (NS > 1), true);                                   \
-            else ISO_LAUNCH7(false, PROF, TRK, false, false, true);                                                      \
-        } else if (NS > 1 && f.seq) ISO_LAUNCH7(CAT, PROF, TRK, PEER, (NS > 1), false);                                  \
-        else ISO_LAUNCH7(CAT, PROF, TRK, PEER, false, false);                                                            \
+            if (NS > 1 && f.seq == 1) ISO_LAUNCH7(false, PROF, TRK, false, (NS > 1 ? 1 : 0), true);                      \
+            else if (NS > 1 && f.seq == 2) ISO_LAUNCH7(false, PROF, TRK, false, (NS > 1 ? 2 : 0), true);                 \
+            else if (NS > 1 && f.seq == 3) ISO_LAUNCH7(false, PROF, TRK, false, (NS > 1 ? 3 : 0), true);                 \
+            else ISO_LAUNCH7(false, PROF, TRK, false, 0, true);                                                          \
+        } else if (NS > 1 && f.seq == 1) ISO_LAUNCH7(CAT, PROF, TRK, PEER, (NS > 1 ? 1 : 0), false);                     \
+        else if (NS > 1 && f.seq == 2) ISO_LAUNCH7(CAT, PROF, TRK, PEER, (NS > 1 ? 2 : 0), false);                       \
+        else if (NS > 1 && f.seq == 3) ISO_LAUNCH7(CAT, PROF, TRK, PEER, (NS > 1 ? 3 : 0), false);                       \
+        else ISO_LAUNCH7(CAT, PROF, TRK, PEER, 0, false);                                                                \
     } while (0)
 #define ISO_LAUNCH3(CAT, PROF, TRK)                                                                                      \
     do {                                                                                                                 \

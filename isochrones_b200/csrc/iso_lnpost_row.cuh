@@ -204,11 +204,11 @@ __device__ __forceinline__ void iso_bc_chunk(const IsoGridDev &bg, const int (&i
 // One row.  want_prior / want_like: the caller asked for the separate lnprior / lnlike values (every term is then
 // evaluated, as BasicStarModel.lnprior / lnlike would); otherwise rows whose prior is already known to be
 // non-finite return lnpost = -inf early, which is exactly what StarModel.lnpost returns (starmodel.py:540-541).
-// SEQ (multiple stars, BC pack of exactly one 4-band chunk): every star's magnitudes are evaluated right after its
-// model cell, so only flux[4] survives from star to star instead of each star's located BC cell (4 indices + 4
-// distances + Mbol): the binary / triple kernels then fit in 128 registers (they spilled 250-350 bytes before).  The
-// arithmetic and its order are those of the chunk-major form, the results bit-identical.
-template <int NSTARS, int PROFILE, bool TRACK, int LAYOUT = ISO_MODEL_LAYOUT, bool SEQ = false>
+// SEQ > 0 (multiple stars, BC pack of exactly SEQ 4-band chunks): every star's magnitudes are evaluated right after
+// its model cell, so only flux[4 * SEQ] survives from star to star instead of each star's located BC cell (4 indices +
+// 4 distances + Mbol): the binary / triple kernels then fit in 128 registers (they spilled 250-350 bytes before).
+// The arithmetic and its order are those of the chunk-major form (SEQ = 0), the results bit-identical.
+template <int NSTARS, int PROFILE, bool TRACK, int LAYOUT = ISO_MODEL_LAYOUT, int SEQ = 0>
 __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, const double2 *s_nodes, const IsoModelDev &m,
                                                        const double (&p)[NSTARS + 4], bool want_prior, bool want_like)
 {
@@ -262,7 +262,10 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
         double Teff = nan, logg = nan, feh_s = nan, nu_max = nan, delta_nu = nan;
         // mags.py:52: 5 log10(d / 10); the default profile already holds log(d)
         const double dist_mod = DEF ? 5.0 * fma(lnd, 0.43429448190325182765, -1.0) : 5.0 * log10(dist / 10.0);
-        double flux[4] = {0.0, 0.0, 0.0, 0.0};   // SEQ: summed fluxes of the (single) band chunk
+        constexpr int NFLUX = SEQ ? 4 * SEQ : 4;
+        double flux[NFLUX];                      // SEQ: summed fluxes of the band chunks
+#pragma unroll
+        for (int b = 0; b < NFLUX; b++) flux[b] = 0.0;
         bool eeps_finite = true;                 // SEQ: every star so far has a finite EEP prior
 #pragma unroll
         for (int k = 0; k < NSTARS; k++) {
@@ -408,19 +411,40 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
                 // is already known to be non-finite and no separate lnlike was asked for (StarModel.lnpost never
                 // evaluates the likelihood then)
                 eeps_finite = eeps_finite && isfinite(lnp_eep[k]);
-                const int cm = m.obs_mask & 0xF;
-                if (cm && (want_like || (eeps_finite && !order_bad && isfinite(cheap)))) {
-                    double mg4[4] = {nan, nan, nan, nan};
-                    if (iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[0], y4[0])) {
-                        double bcv[4];
-                        iso_bc_chunk(bg, idx4[0], y4[0], 0, bcv);
-                        const double mb = v[ISO_MP_MBOL] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
+                if constexpr (SEQ == 1) {
+                    const int cm = m.obs_mask & 0xF;
+                    if (cm && (want_like || (eeps_finite && !order_bad && isfinite(cheap)))) {
+                        double mg4[4] = {nan, nan, nan, nan};
+                        if (iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[0], y4[0])) {
+                            double bcv[4];
+                            iso_bc_chunk(bg, idx4[0], y4[0], 0, bcv);
+                            const double mb = v[ISO_MP_MBOL] + dist_mod;   // mags.py:59: Mbol + dist_mod - bc
 #pragma unroll
-                        for (int b = 0; b < 4; b++) mg4[b] = mb - bcv[b];
+                            for (int b = 0; b < 4; b++) mg4[b] = mb - bcv[b];
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
                     }
+                } else if (m.obs_mask && (want_like || (eeps_finite && !order_bad && isfinite(cheap)))) {
+                    // several chunks: the located BC cell serves them one after the other
+                    const bool located = iso_locate_smem<4>(bg, s_nodes, G.smem_axis_off[1], x4, idx4[0], y4[0]);
+                    const double mb = v[ISO_MP_MBOL] + dist_mod;
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
-                        if (cm & (1 << b)) flux[b] += exp10(-0.4 * mg4[b]);
+                    for (int ch = 0; ch < SEQ; ch++) {
+                        const int cm = (m.obs_mask >> (4 * ch)) & 0xF;
+                        if (!cm) continue;
+                        double mg4[4] = {nan, nan, nan, nan};
+                        if (located) {
+                            double bcv[4];
+                            iso_bc_chunk(bg, idx4[0], y4[0], ch, bcv);
+#pragma unroll
+                            for (int b = 0; b < 4; b++) mg4[b] = mb - bcv[b];
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (cm & (1 << b)) flux[4 * ch + b] += exp10(-0.4 * mg4[b]);
+                    }
                 }
             }
         }
@@ -455,10 +479,10 @@ __device__ __forceinline__ IsoRowResult iso_lnpost_row(const IsoRowGrids &G, con
         if (m.spec_mask & 2) ll += iso_gauss(m.spec[1], logg);
         if (m.spec_mask & 4) ll += iso_gauss(m.spec[2], feh_s);
         if (SEQ) {
-            const int cm = m.obs_mask & 0xF;
+            const int om = m.obs_mask & ((1 << NFLUX) - 1);
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (cm & (1 << b)) ll += iso_gauss(m.mag[b], -2.5 * log10(flux[b]));
+            for (int b = 0; b < NFLUX; b++)
+                if (om & (1 << b)) ll += iso_gauss(m.mag[b], -2.5 * log10(flux[b]));
         } else if (m.obs_mask) {
             for (int ch = 0; ch < bc_chunks; ch++) {
                 const int cm = (m.obs_mask >> (4 * ch)) & 0xF;

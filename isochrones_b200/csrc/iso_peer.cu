@@ -208,6 +208,9 @@ int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const 
     t.step = step;
     t.done = g->d_done;
     t.offset = (long long)g->rank * g->pad;
+    t.own_flags = ISO_PEER_INKERNEL_WAIT ? g->d_flags : nullptr;
+    t.timeout_ns = g->timeout_ns;
+    t.err = g->d_err;
     for (int r = 0; r < ISO_MAX_PEERS; r++) {
         t.out[r] = r < g->nranks ? g->peer_recv[r] + half : nullptr;
         t.flags[r] = r < g->nranks ? g->peer_flags[r] : nullptr;
@@ -222,8 +225,10 @@ int iso_lnpost_allgather_device(iso_ctx *ctx, const iso_grid *model_pack, const 
         iso_peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(t);
         ctx->launches += 1;
     }
-    iso_peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_flags, g->nranks, step, g->timeout_ns, g->d_err);
-    ctx->launches += 1;
+    if (!ISO_PEER_INKERNEL_WAIT || N == 0) {
+        iso_peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_flags, g->nranks, step, g->timeout_ns, g->d_err);
+        ctx->launches += 1;
+    }
     ISO_CUDA(ctx, cudaGetLastError());
     if (d_gathered) *d_gathered = g->d_recv + half;
     return ISO_OK;

@@ -139,9 +139,10 @@ class DeviceEnsembleSampler(object):
 
 class ShardedEnsembleSampler(object):
     """ONE ensemble of walkers sharded over the GPUs of a node (``iso_ensemble_*``): every rank (one process per GPU)
-    constructs this with the SAME ``p0`` and ``seed``; per half-step a rank moves only its block of the active half and
-    its kernel writes every accepted walker into the ensemble copy of every rank over NVLink peer mappings — the
-    acceptance step's exchange fused into the evaluation, no collective launch.  The chain is the one
+    constructs this with the SAME ``p0`` and ``seed``; per half-step a rank moves only its block of the active half, and
+    each proposal gathers its partner walker from the HBM of the rank that owns it over NVLink peer mappings — the
+    acceptance step's exchange fused into the evaluation, no collective launch; a run ends with one
+    replication of every rank's blocks, so ``state()`` reads the whole ensemble locally.  The chain is the one
     ``DeviceEnsembleSampler`` produces for the same seed, bit for bit, whatever the number of ranks; ensembles are not
     bounded by shared memory (1e5 - 1e6 walkers).
 

@@ -85,6 +85,33 @@ def test_lnpost_vs_oracle_full_grids(world, kind, N):
     assert np.array_equal(mod.lnpost_batch(pars), lnpost, equal_nan=True)
 
 
+MANY_BANDS = ("J", "H", "K", "G", "BP", "RP", "W1", "W2", "W3", "TESS", "Kepler", "V", "B", "u")
+
+
+@pytest.mark.parametrize("N,n_bands", [(2, 7), (3, 7), (2, 11), (3, 11), (2, 14), (3, 5)])
+def test_multi_star_band_chunks_vs_oracle(world, N, n_bands):
+    """Binaries / triples whose BC pack holds 2, 3 and 4 chunks of four bands: the star-sequential kernels for up to three
+    chunks, the chunk-major form beyond; summed fluxes (utils.py:67-75) in the reference's star order either way."""
+    import isochrones_b200 as ib
+    from isochrones_b200 import synthetic as syn
+    from oracle import oracle
+
+    bands = MANY_BANDS[:n_bands]
+    bc = syn.make_bc_grid(bands=bands)
+    w = {"ic_iso": ib.ichrone_from_arrays("iso", world["iso"], bc, ctx=world["ctx"]), "og_iso": world["og_iso"],
+         "og_bc": oracle.Grid(bc["grid"], bc["axes"])}
+    mod, om, truth = _model(w, "iso", N, bands=bands)
+    assert len(mod.bands) == n_bands
+    pars = _batches("iso", mod, truth, world["iso"]["axes"], 12_000)
+    got = mod.lnpost_batch(pars, parts=True)
+    want = om.lnpost_batch(pars, n_threads=8, parts=True)
+    _compare(got[1], want[1], 1e-9)
+    _compare(got[2], want[2], ATOL_LNPOST)
+    _compare(got[0], want[0], ATOL_LNPOST)
+    assert np.isfinite(want[0]).sum() > 8_000
+    assert np.array_equal(mod.lnpost_batch(pars), got[0], equal_nan=True)
+
+
 def test_seismology_and_bands_vs_oracle(world):
     mod, om, truth = _model(world, "track", 1, bands=("G", "BP", "RP", "J", "H", "K", "V"),
                             nu_max=(3000.0, 60.0), delta_nu=(130.0, 2.0))

@@ -40,7 +40,7 @@ def main():
         ("scattered", mod, lambda s: bench.scattered_batch(n, seed=50 + s)),
         ("grid_wide", mod, lambda s: bench.grid_wide_batch(n, trk, seed=90 + s)),
     ]
-    extra = {"binary", "iso_single", "iso_prior", "catalog", "chains", "one_chain"}
+    extra = {"binary", "binary8", "binary11", "iso_single", "iso_prior", "catalog", "chains", "one_chain"}
     if only is None or only & extra:
         iso = syn.make_iso_grid(columns=("Teff", "logg", "feh", "Mbol", "mass", "dm_deep", "nu_max", "delta_nu"))
         ici = ib.ichrone_from_arrays("iso", iso, bc, ctx=ctx)
@@ -59,6 +59,15 @@ def main():
         single = ib.SingleStarModel(ici, Teff=(5772.0, 80.0), logg=(4.44, 0.1), feh=(0.0, 0.1), parallax=(10.0, 0.1),
                                     **{b: (float(np.round(m, 3)), 0.02) for b, m in zip(bench.BANDS, m1)})
         b1 = [single.bounds(p) for p in single.param_names]
+        if only is not None and only & {"binary8", "binary11"}:
+            many = ("J", "H", "K", "G", "BP", "RP", "W1", "W2", "W3", "TESS", "Kepler")
+            for nb in (8, 11):
+                bcn = syn.make_bc_grid(bands=many[:nb])
+                icn = ib.ichrone_from_arrays("iso", iso, bcn, ctx=ctx)
+                _, _, _, mn = icn.interp_mag([t2[0]] + list(t2[2:]), list(many[:nb]))
+                obsn = {b: (float(np.round(m, 3)) - 0.35, 0.02) for b, m in zip(many[:nb], mn)}
+                work.append(("binary%d" % nb, ib.BinaryStarModel(icn, Teff=(5772.0, 80.0), logg=(4.44, 0.1), feh=(0.0, 0.1),
+                                                                parallax=(10.0, 0.1), **obsn), bin_batch))
         work += [("binary", binary, bin_batch),
                  ("iso_single", single, lambda s: syn.posterior_like_batch("iso", n, t1, seed=170 + s)),
                  ("iso_prior", single, lambda s: syn.prior_like_batch("iso", n, b1, seed=270 + s))]
