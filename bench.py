@@ -919,9 +919,10 @@ def extra_workloads(ctx, bc, args, peak, rk):
             "value": res.n_evals / dt, "unit": UNIT, "seconds": dt, "n_evals": res.n_evals, "n_iter": res.n_iter,
             "logZ": res.logZ, "logZ_err": res.logZ_err, "information_nats": res.information, "efficiency": res.efficiency,
             "finite_fraction_of_prior_box": res.finite_fraction, "converged": res.converged,
+            "n_launches": res.n_batches + 1, "n_ellipsoids_max": res.n_ellipsoids_max,
             "posterior_mean": [float(v) for v in res.mean()], "posterior_std": [float(v) for v in res.std()],
             "config": "BasicStarModel.fit_nested on the isochrone-grid single star over the full prior box: host-driven nested "
-                      "sampling (single bounding ellipsoid), every batch of 8192 candidate live points = one "
+                      "sampling (MultiNest-style union of bounding ellipsoids), every batch of 8192 candidate live points = one "
                       "iso_mnest_lnpost_batch launch (cube -> parameters -> lnpost)"}
     return out
 
