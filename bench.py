@@ -946,20 +946,16 @@ def eleven_band_workload(ctx, trk, truth, n_eep, args, peak):
 # ---------------------------------------------------------------------------------------------------------------------
 # multi-GPU
 # ---------------------------------------------------------------------------------------------------------------------
-def make_peer_group(ctx, rk, rows_per_rank):
-    """PeerGather on every rank, or None on every rank (the ranks agree, so that nobody waits alone)."""
+def make_peer_group(ctx, rk, rows_per_rank, comm):
+    """The library's own choice of the per-step exchange (parallel.row_gather: all ranks decide together): the fused
+    PeerGather, or (None, why) when it handed out the NCCL form — which the bench times separately anyway."""
     from isochrones_b200 import parallel
 
-    peer, err = None, ""
-    try:
-        peer = parallel.PeerGather(ctx, rk.rank, rk.world, rows_per_rank, rk.allgather_bytes)
-    except Exception as e:   # e.g. CUDA IPC not permitted in this container
-        err = repr(e)[:300]
-    if not rk.all(peer is not None):
-        if peer is not None:
-            peer.close()
-        return None, err or "peer setup failed on another rank"
-    return peer, ""
+    g, why = parallel.row_gather(ctx, rk.rank, rk.world, rows_per_rank, rk.allgather_bytes, comm=comm)
+    if isinstance(g, parallel.PeerGather):
+        return g, ""
+    g.close()
+    return None, why or "peer setup failed"
 
 
 def multi_gpu(ctx, compiled, d_post, d_out, bc, args, rk, h_in, h_out, mod):
@@ -996,7 +992,7 @@ def multi_gpu(ctx, compiled, d_post, d_out, bc, args, rk, h_in, h_out, mod):
     ms_g = timed(nccl_step, nccl_step)
     ag = {"ms_per_step_with_gather": ms_g, "value_with_gather": world * BATCH / (ms_g * 1e-3),
           "bytes_per_rank_per_step": BATCH * 8, "collective": "ncclAllGather f64 on the compute stream"}
-    peer, err = make_peer_group(ctx, rk, BATCH)
+    peer, err = make_peer_group(ctx, rk, BATCH, comm)
     identical = None
     if peer is None:
         ag["fused_peer_store"] = {"unavailable": err}
@@ -1040,7 +1036,7 @@ def multi_gpu(ctx, compiled, d_post, d_out, bc, args, rk, h_in, h_out, mod):
     ctx.d2h(got, d_all)
     full = sh.assemble(got)
     ms_f, same = None, None
-    peer, _ = make_peer_group(ctx, rk, sh.pad)
+    peer, _ = make_peer_group(ctx, rk, sh.pad, comm)
     if peer is not None:
         got_f = np.empty((world, sh.pad))
         ctx.d2h(got_f, peer.lnpost(binary.compiled, d_p, n_mine))

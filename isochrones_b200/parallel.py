@@ -245,11 +245,25 @@ class PeerGather(object):
     def __init__(self, ctx, rank, world, rows_per_rank, allgather_bytes):
         self.ctx, self.rank, self.world, self.pad = ctx, int(rank), int(world), int(rows_per_rank)
         self.handle = C.c_void_p()
-        ctx.check(_lib.lib().iso_peer_create(ctx.handle, self.rank, self.world, self.pad, C.byref(self.handle)))
+        failed = None
+        try:
+            ctx.check(_lib.lib().iso_peer_create(ctx.handle, self.rank, self.world, self.pad, C.byref(self.handle)))
+        except Exception as e:
+            if self.world == 1:
+                raise
+            failed = e
         if self.world > 1:
             buf = C.create_string_buffer(128)
-            ctx.check(_lib.lib().iso_peer_export(ctx.handle, self.handle, buf))
-            handles = allgather_bytes(bytes(buf.raw))
+            if failed is None:
+                try:
+                    ctx.check(_lib.lib().iso_peer_export(ctx.handle, self.handle, buf))
+                except Exception as e:
+                    failed = e
+            # a rank that could not create / export still joins the exchange (with zeros) before it raises
+            handles = allgather_bytes(bytes(buf.raw) if failed is None else bytes(128))
+            if failed is not None:
+                self.close()
+                raise failed
             if len(handles) != self.world or any(len(h) != 128 for h in handles):
                 raise ValueError("the handle exchange must return one 128-byte payload per rank")
             blob = C.create_string_buffer(b"".join(handles), 128 * self.world)
@@ -277,6 +291,82 @@ class PeerGather(object):
         if self.handle:
             _lib.lib().iso_peer_destroy(self.ctx.handle, self.handle)
             self.handle = C.c_void_p()
+
+
+class NcclRowGather(object):
+    """``PeerGather``'s interface on the library collective: the lnpost kernel writes this rank's block to a device
+    buffer, ``ncclAllGather`` (on the same stream) distributes it.  What ``row_gather`` hands out when the GPUs of the
+    node cannot map each other's memory (no peer access, CUDA IPC refused by the container)."""
+
+    def __init__(self, ctx, rank, world, rows_per_rank, comm, own_comm=False):
+        self.ctx, self.rank, self.world, self.pad, self.comm = ctx, int(rank), int(world), int(rows_per_rank), comm
+        self._own_comm = own_comm
+        self.d_own = ctx.dev_alloc(self.pad * 8)
+        self.d_all = ctx.dev_alloc(self.world * self.pad * 8)
+        ctx.memset(self.d_own, 0xFF, self.pad * 8)          # padding rows read as NaN
+
+    def lnpost(self, compiled, d_pars, n, d_model_of_row=None):
+        if int(n) > self.pad:
+            raise ValueError("more rows than the gather was created for")
+        compiled.lnpost_device(d_pars, int(n), self.d_own, d_model_of_row=d_model_of_row)
+        self.comm.allgather(self.d_own, self.pad, self.d_all)
+        return self.d_all
+
+    def set_timeout(self, seconds):
+        pass                     # NCCL has its own watchdog
+
+    def check(self):
+        self.ctx.sync()
+
+    def close(self):
+        if self.d_own:
+            self.ctx.dev_free(self.d_own)
+            self.ctx.dev_free(self.d_all)
+            self.d_own = self.d_all = None
+            if self._own_comm:
+                self.comm.close()
+
+
+def row_gather(ctx, rank, world, rows_per_rank, allgather_bytes, broadcast=None, comm=None, make_peer=None):
+    """The per-step exchange of a host-driven sampler, chosen ONCE and by ALL ranks together: the fused peer-store
+    gather when every rank could map every other rank's buffers, otherwise ``NcclRowGather`` (``comm``: an existing
+    ``NcclGather``, or ``broadcast`` to create one).  Every rank takes part in every exchange of the decision, also a
+    rank whose own setup failed — nobody waits alone.  Returns ``(gather, reason)``; ``reason`` is empty for the fused
+    path and says why not otherwise."""
+    make_peer = make_peer or (lambda: PeerGather(ctx, rank, world, rows_per_rank, _agreeing(allgather_bytes)))
+    peer, why = None, ""
+    try:
+        peer = make_peer()
+    except _PeerSetupFailed as e:        # some rank could not create / export its buffers: every rank lands here
+        why = str(e)
+    except Exception as e:               # this rank could not connect (the others may have)
+        why = repr(e)[:300]
+    verdicts = allgather_bytes(b"1" if peer is not None else b"0" + why.encode()[:200])
+    if all(v[:1] == b"1" for v in verdicts):
+        return peer, ""
+    if peer is not None:
+        peer.close()
+    reason = why or next(v[1:].decode(errors="replace") for v in verdicts if v[:1] != b"1") or "peer setup failed on another rank"
+    if comm is None:
+        if broadcast is None:
+            raise ValueError("row_gather: the fused path is unavailable (%s) and neither comm nor broadcast was given" % reason)
+        return NcclRowGather(ctx, rank, world, rows_per_rank, NcclGather(ctx, rank, world, exchange=broadcast), own_comm=True), reason
+    return NcclRowGather(ctx, rank, world, rows_per_rank, comm), reason
+
+
+class _PeerSetupFailed(RuntimeError):
+    pass
+
+
+def _agreeing(allgather_bytes):
+    """Handle exchange in which a rank that has nothing to export still takes part: ``PeerGather`` ships its 128-byte
+    handle through this; a failed rank ships zeros and every rank raises together."""
+    def exchange(payload):
+        out = allgather_bytes(payload)
+        if any(len(h) != 128 or not any(h) for h in out):
+            raise _PeerSetupFailed("a rank could not export its peer buffers")
+        return out
+    return exchange
 
 
 def sharded_lnpost(compiled, pars, sharder, gather):

@@ -3,7 +3,9 @@ WORLD_SIZE / ISO_B200_RDZV in the environment, no torch).  Rank r runs on GPU ``
 GPU both ranks share it (separate processes, CUDA-IPC mappings of each other's buffers), with two they use NVLink.
 
     mode "gather":  fused lnpost + peer all-gather over several steps vs a plain evaluation of all rows;
-    mode "timeout": rank 1 stops publishing steps; rank 0's bounded wait must turn into ISO_E_TIMEOUT, not a hang."""
+    mode "timeout": rank 1 stops publishing steps; rank 0's bounded wait must turn into ISO_E_TIMEOUT, not a hang;
+    mode "fallback": rank 1's peer setup fails: parallel.row_gather moves ALL ranks to kernel + ncclAllGather (needs one
+                     GPU per rank), same results."""
 import os
 import sys
 
@@ -29,7 +31,21 @@ def main():
     mod = ib.BasicStarModel(ic, Teff=(5772.0, 80.0), parallax=(10.0, 0.1), **{b: (float(m), 0.02) for b, m in zip("VJHK", mags)})
     n_total = 10_003                                      # ragged: the last rank's block is shorter than the pad
     sh = parallel.RowSharder(n_total, world, rank)
-    peer = parallel.PeerGather(ctx, rank, world, sh.pad, rdzv.allgather_bytes)
+    if mode == "fallback":
+        def failing():
+            if rank == 1:
+                raise RuntimeError("peer access refused (forced by the test)")
+            return parallel.PeerGather(ctx, rank, world, sh.pad, parallel._agreeing(rdzv.allgather_bytes))
+
+        # rank 1 never reaches the handle exchange, so the other ranks' exchange must not wait for it: they ship their
+        # handles only after everyone has reported in
+        ok = rdzv.allgather_bytes(b"0" if rank == 1 else b"1")
+        make_peer = failing if all(v == b"1" for v in ok) else (lambda: (_ for _ in ()).throw(RuntimeError("peer access refused")))
+        peer, why = parallel.row_gather(ctx, rank, world, sh.pad, rdzv.allgather_bytes, broadcast=rdzv.broadcast, make_peer=make_peer)
+        assert isinstance(peer, parallel.NcclRowGather) and "refused" in why, (type(peer), why)
+    else:
+        peer, why = parallel.row_gather(ctx, rank, world, sh.pad, rdzv.allgather_bytes, broadcast=rdzv.broadcast)
+        assert isinstance(peer, parallel.PeerGather), why
     if mode == "timeout":
         peer.set_timeout(1.0)
     n_steps = 5

@@ -97,3 +97,15 @@ def test_missing_rank_times_out_instead_of_hanging():
     outs = _run_ranks("timeout")
     assert outs[0][0] == 0 and "rank 0 timeout reported" in outs[0][1], outs[0][1][-3000:]
     assert outs[1][0] == 0, outs[1][1][-3000:]
+
+
+def test_failed_peer_setup_moves_every_rank_to_nccl():
+    """`parallel.row_gather`: one rank cannot map its peers -> ALL ranks use kernel + ncclAllGather, same results.  NCCL
+    needs one GPU per rank, so this runs on multi-GPU boxes only (the decision logic itself: tests/test_sharding_gloo.py)."""
+    from isochrones_b200 import _lib
+
+    if _lib.device_count() < 2:
+        pytest.skip("ncclAllGather needs one GPU per rank")
+    outs = _run_ranks("fallback")
+    for r, (rc, out) in enumerate(outs):
+        assert rc == 0 and ("rank %d ok" % r) in out, out[-3000:]

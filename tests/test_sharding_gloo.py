@@ -78,3 +78,65 @@ def test_sharded_lnpost_world2(n_rows):
     res = sorted(ret.get(timeout=5) for _ in range(2))
     assert [r[1] for r in res] == [True, True]
     assert sum(r[2] for r in res) == n_rows          # every row evaluated exactly once across the ranks
+
+
+def test_row_gather_decision_is_collective():
+    """`parallel.row_gather`: every rank ends up with the same kind of gather; one rank failing its peer setup moves
+    ALL ranks to the NCCL form (stand-ins for the device objects: the decision logic is host code)."""
+    import threading
+
+    from isochrones_b200 import parallel
+
+    world = 3
+    barrier = threading.Barrier(world)
+    slots = {}
+    lock = threading.Lock()
+
+    def make_allgather(rank):
+        state = {"round": 0}
+
+        def allgather(payload):
+            r = state["round"]
+            state["round"] += 1
+            with lock:
+                slots.setdefault(r, {})[rank] = payload
+            barrier.wait()
+            return [slots[r][k] for k in range(world)]
+        return allgather
+
+    class FakePeer(object):
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    class FakeCtx(object):
+        def dev_alloc(self, n):
+            return n
+
+        def dev_free(self, p):
+            pass
+
+        def memset(self, *a):
+            pass
+
+    def run(fail_rank, results):
+        def worker(rank):
+            def make_peer():
+                if rank == fail_rank:
+                    raise RuntimeError("cudaIpcOpenMemHandle: peer access not supported")
+                return FakePeer()
+            g, why = parallel.row_gather(FakeCtx(), rank, world, 128, make_allgather(rank), comm=object(), make_peer=make_peer)
+            results[rank] = (type(g).__name__, why)
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        [t.start() for t in ts]
+        [t.join(30) for t in ts]
+
+    res = {}
+    run(None, res)
+    assert all(res[r] == ("FakePeer", "") for r in range(world)), res
+    slots.clear()
+    res = {}
+    run(1, res)
+    assert all(res[r][0] == "NcclRowGather" for r in range(world)), res
+    assert all("peer access not supported" in res[r][1] for r in range(world)), res
