@@ -40,6 +40,24 @@ def main():
         ("scattered", mod, lambda s: bench.scattered_batch(n, seed=50 + s)),
         ("grid_wide", mod, lambda s: bench.grid_wide_batch(n, trk, seed=90 + s)),
     ]
+    if only is not None and only & {"posterior_sorted", "grid_wide_sorted", "prior_sorted", "scattered_sorted", "posterior_warpsorted"}:
+        ax = trk["axes"]                                   # (feh, mass, eep) axes of the track grid
+
+        def cell_sorted(gen, block=None):
+            def make(s):
+                b = gen(s)
+                key = (np.searchsorted(ax[0], b[:, 2]) * 4096 + np.searchsorted(ax[1], b[:, 0])) * 4096 + np.searchsorted(ax[2], b[:, 1])
+                if block is None:
+                    return b[np.argsort(key, kind="stable")]
+                out = b.copy()                             # sorted inside blocks of `block` rows only (what a CTA could do)
+                for i in range(0, len(b), block):
+                    out[i:i + block] = b[i:i + block][np.argsort(key[i:i + block], kind="stable")]
+                return out
+            return make
+        base = {n_: g_ for n_, _, g_ in work}
+        work += [("posterior_sorted", mod, cell_sorted(base["posterior"])), ("grid_wide_sorted", mod, cell_sorted(base["grid_wide"])),
+                 ("prior_sorted", mod, cell_sorted(base["prior"])), ("scattered_sorted", mod, cell_sorted(base["scattered"])),
+                 ("posterior_warpsorted", mod, cell_sorted(base["posterior"], block=8192))]
     extra = {"binary", "binary8", "binary11", "iso_single", "iso_prior", "catalog", "chains", "one_chain"}
     if only is None or only & extra:
         iso = syn.make_iso_grid(columns=("Teff", "logg", "feh", "Mbol", "mass", "dm_deep", "nu_max", "delta_nu"))
