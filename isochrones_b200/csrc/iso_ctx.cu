@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "iso_common.cuh"
+#include "iso_scratch.cuh"
 
 static thread_local std::string g_last_error;  // failures of calls that had no context
 
@@ -92,6 +93,12 @@ int iso_ctx_create(int device, iso_ctx **out)
     }
     CTX_TRY(cudaEventCreate(&ctx->ev_start));
     CTX_TRY(cudaEventCreate(&ctx->ev_stop));
+    {   // scratch allocations (iso_scratch_alloc) come from the device's default pool; let it keep freed blocks
+        cudaMemPool_t pool;
+        CTX_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = 1ull << 30;
+        CTX_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CTX_TRY(cudaMalloc(&ctx->d_claim, ISO_CLAIM_SLOTS * ISO_CLAIM_STRIDE * sizeof(unsigned long long)));
     CTX_TRY(cudaMemset(ctx->d_claim, 0, ISO_CLAIM_SLOTS * ISO_CLAIM_STRIDE * sizeof(unsigned long long)));
 #undef CTX_TRY
@@ -144,6 +151,23 @@ int iso_ctx_info(iso_ctx *ctx, char *name, int *sm_count, int64_t *l2_bytes, int
     if (cc) *cc = ctx->prop.major * 10 + ctx->prop.minor;
     return ISO_OK;
 }
+
+}  // extern "C"
+
+cudaError_t iso_scratch_alloc(iso_ctx *ctx, void **d_ptr, size_t bytes)
+{
+    *d_ptr = nullptr;
+    cudaError_t e = cudaMallocAsync(d_ptr, bytes > 0 ? bytes : 1, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // allocated for every stream, not only ours
+    return e;
+}
+
+void iso_scratch_free(iso_ctx *ctx, void *d_ptr)
+{
+    if (d_ptr) cudaFreeAsync(d_ptr, ctx->stream);
+}
+
+extern "C" {
 
 int iso_dev_alloc(iso_ctx *ctx, int64_t bytes, void **d_ptr)
 {

@@ -28,6 +28,7 @@
 
 #include "iso_lnpost_row.cuh"
 #include "iso_stretch.cuh"
+#include "iso_scratch.cuh"
 
 struct iso_ensemble {
     const iso_grid *mp = nullptr, *bp = nullptr;
@@ -426,11 +427,11 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     const long long n_keep = n_steps / thin;
     const size_t pos_n = (size_t)e->n_walkers * e->ndim;
     double *d_chain = nullptr, *d_lp = nullptr;
-    if (h_chain && n_keep > 0) ISO_CUDA(ctx, cudaMalloc(&d_chain, (size_t)n_keep * pos_n * sizeof(double)));
+    if (h_chain && n_keep > 0) ISO_CUDA(ctx, iso_scratch_alloc(ctx, (void **)&d_chain, (size_t)n_keep * pos_n * sizeof(double)));
     if (h_lnprob && n_keep > 0) {
-        cudaError_t ce = cudaMalloc(&d_lp, (size_t)n_keep * e->n_walkers * sizeof(double));
+        cudaError_t ce = iso_scratch_alloc(ctx, (void **)&d_lp, (size_t)n_keep * e->n_walkers * sizeof(double));
         if (ce != cudaSuccess) {
-            if (d_chain) cudaFree(d_chain);
+            iso_scratch_free(ctx, d_chain);
             return iso_check_cuda(ctx, ce, "iso_ensemble_run");
         }
     }
@@ -518,8 +519,8 @@ int iso_ensemble_run(iso_ctx *ctx, iso_ensemble *e, int n_steps, int thin, doubl
     if (ce == cudaSuccess && d_lp)
         ce = cudaMemcpyAsync(h_lnprob, d_lp, (size_t)n_keep * e->n_walkers * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    if (d_chain) cudaFree(d_chain);
-    if (d_lp) cudaFree(d_lp);
+    iso_scratch_free(ctx, d_chain);
+    iso_scratch_free(ctx, d_lp);
     if (ce != cudaSuccess) return iso_check_cuda(ctx, ce, "iso_ensemble_run");
     e->step += n_steps;
     return ensemble_timed_out(ctx, e);

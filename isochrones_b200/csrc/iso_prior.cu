@@ -1,6 +1,7 @@
 // isochrones_b200 — vector evaluation of one prior object: lnpdf(x) / __call__(x) of priors.py (see iso_prior.cuh).
 #include "iso_common.cuh"
 #include "iso_prior.cuh"
+#include "iso_scratch.cuh"
 
 __global__ void iso_prior_eval_kernel(const iso_prior *__restrict__ prior, int which, const double *__restrict__ x,
                                       double *__restrict__ out, long long N)
@@ -44,15 +45,15 @@ extern "C" int iso_prior_eval(iso_ctx *ctx, const iso_prior *prior, int which, c
     iso_prior filled = *prior;
     iso_prior_fill(&filled);
     iso_prior *d_prior = nullptr;
-    ISO_CUDA(ctx, cudaMalloc(&d_prior, sizeof(iso_prior)));
+    ISO_CUDA(ctx, iso_scratch_alloc(ctx, (void **)&d_prior, sizeof(iso_prior)));
     cudaError_t e = cudaMemcpy(d_prior, &filled, sizeof(iso_prior), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-        cudaFree(d_prior);
+        iso_scratch_free(ctx, d_prior);
         return iso_check_cuda(ctx, e, "iso_prior_eval");
     }
     IsoPipeArray arr[2] = {IsoPipeArray{h_x, nullptr, 8}, IsoPipeArray{nullptr, h_out, 8}};
     PriorUser u{d_prior, which};
-    int rc = iso_run_pipeline(ctx, N, arr, 2, prior_launch, &u);
-    cudaFree(d_prior);
+    int rc = iso_run_pipeline(ctx, N, arr, 2, prior_launch, &u);   // returns with every stream of the pipeline waited for
+    iso_scratch_free(ctx, d_prior);
     return rc;
 }

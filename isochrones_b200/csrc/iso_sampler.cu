@@ -17,6 +17,7 @@
 
 #include "iso_lnpost_row.cuh"
 #include "iso_stretch.cuh"
+#include "iso_scratch.cuh"
 
 #ifndef ISO_SAMPLER_SEG_STEPS
 #define ISO_SAMPLER_SEG_STEPS 16   // steps a CTA advances a claimed chain by before it hands it back (multi-wave runs)
@@ -289,11 +290,11 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     const long long n_keep = n_steps / thin;
     const size_t rows = (size_t)s->n_chains * s->n_walkers;
     double *d_chain = nullptr, *d_lp = nullptr;
-    if (h_chain && n_keep > 0) ISO_CUDA(ctx, cudaMalloc(&d_chain, (size_t)n_keep * rows * s->ndim * sizeof(double)));
+    if (h_chain && n_keep > 0) ISO_CUDA(ctx, iso_scratch_alloc(ctx, (void **)&d_chain, (size_t)n_keep * rows * s->ndim * sizeof(double)));
     if (h_lnprob && n_keep > 0) {
-        cudaError_t e = cudaMalloc(&d_lp, (size_t)n_keep * rows * sizeof(double));
+        cudaError_t e = iso_scratch_alloc(ctx, (void **)&d_lp, (size_t)n_keep * rows * sizeof(double));
         if (e != cudaSuccess) {
-            if (d_chain) cudaFree(d_chain);
+            iso_scratch_free(ctx, d_chain);
             return iso_check_cuda(ctx, e, "iso_sampler_run");
         }
     }
@@ -387,8 +388,8 @@ int iso_sampler_run(iso_ctx *ctx, iso_sampler *s, int n_steps, int thin, double 
     if (e == cudaSuccess && d_lp)
         e = cudaMemcpyAsync(h_lnprob, d_lp, (size_t)n_keep * rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (d_chain) cudaFree(d_chain);
-    if (d_lp) cudaFree(d_lp);
+    iso_scratch_free(ctx, d_chain);
+    iso_scratch_free(ctx, d_lp);
     if (e != cudaSuccess) return iso_check_cuda(ctx, e, "iso_sampler_run");
     s->step += n_steps;
     return ISO_OK;
