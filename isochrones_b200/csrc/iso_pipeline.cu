@@ -245,8 +245,12 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
     for (int s = 0; s < n_slots; s++) ISO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream[s], ctx->ev_copy[0], 0));
 
     PipeSlot slots[2];
-    auto finalize = [&](int s) -> int {
+    // A slot is reused by chunk c + 2 on the SAME stream, so the device side needs no host wait; the host waits only
+    // where it has work of its own on the slot's page-locked staging buffer (pageable caller arrays), and at the end.
+    // With page-locked caller arrays every chunk is queued at once.
+    auto finalize = [&](int s, bool last) -> int {
         if (!slots[s].busy) return ISO_OK;
+        if (!any_pageable && !last) return ISO_OK;
         ISO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[s]));
         for (int k = 0; k < n_arrays; k++) {
             if (!active[k] || pinned[k] || !arrays[k].h_out) continue;
@@ -259,11 +263,13 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
 
     // Chunk schedule: full chunks while more than one chunk of rows remains, then halves of what is left (down to
     // ISO_PIPE_TAIL_ROWS): the transfers are the bottleneck, and whatever the LAST chunk's kernel and result copy take
-    // cannot overlap anything — so the last chunk is made small.
+    // cannot overlap anything — so the last chunk is made small, but not too small: every chunk costs ~11 us of copy-engine
+    // idle time (measured: 1e6 rows, 40 B in / 8 B out per row, bare H2D 0.735 ms: tail 16 k 0.865 ms, 64 k 0.848,
+    // 128 k 0.838; profiles/r2x_e2e_chunk_probe.txt).
     static const int64_t tail_rows = [] {
         const char *e = getenv("ISO_PIPE_TAIL_ROWS");
         long long v = e ? atoll(e) : 0;
-        return (int64_t)(v >= 1024 ? v : 16384);
+        return (int64_t)(v >= 1024 ? v : 131072);
     }();
     int c = 0;
     int64_t n = 0;
@@ -273,7 +279,7 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         if (left > chunk) n = chunk;
         else if (left > 2 * tail_rows && n_rows > chunk) n = (left / 2 + 4095) & ~(int64_t)4095;
         else n = left;
-        int rc = finalize(s);
+        int rc = finalize(s, false);
         if (rc != ISO_OK) return rc;
         cudaStream_t st = ctx->copy_stream[s];
         void *d_arrays[ISO_PIPE_MAX_ARRAYS];
@@ -301,7 +307,7 @@ int iso_run_pipeline(iso_ctx *ctx, int64_t n_rows, const IsoPipeArray *arrays, i
         slots[s].busy = true;
     }
     for (int s = 0; s < n_slots; s++) {
-        int rc = finalize(s);
+        int rc = finalize(s, true);
         if (rc != ISO_OK) return rc;
     }
     return ISO_OK;
