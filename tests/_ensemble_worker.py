@@ -1,6 +1,9 @@
 """Worker of tests/test_gpu_ensemble.py — one process per rank (RANK / WORLD_SIZE / ISO_B200_RDZV in the environment,
 no torch; rank r on GPU r % device_count): the sharded ensemble sampler against the one-GPU persistent sampler run on
-this rank's own GPU with the same seed.  The two must agree bit for bit on every kept ensemble."""
+this rank's own GPU with the same seed.  The two must agree bit for bit on every kept ensemble.
+
+    mode "timeout": rank 1 stops taking part after the first run; rank 0's next run must end with ISO_E_TIMEOUT (bounded
+    waits in the half-step kernels), not hang."""
 import os
 import sys
 
@@ -30,6 +33,22 @@ def main():
     ref.run_mcmc(steps, thin=thin)
     ens = ShardedEnsembleSampler(mod.compiled, nw, p0, seed=77, rank=rank, world=world, allgather_bytes=rdzv.allgather_bytes)
     ens.run_mcmc(steps // 2, thin=thin)                  # two runs: the step counter and flags carry over
+    if len(sys.argv) > 1 and sys.argv[1] == "timeout":
+        if rank == 0:
+            ens.set_timeout(0.5)
+            try:
+                ens.run_mcmc(1, store=False, fetch=False)
+            except _lib.IsoError as e:
+                assert e.code == -6 and "rank 1" in str(e), str(e)
+                print("rank 0 timeout reported", flush=True)
+            else:
+                raise AssertionError("no timeout reported")
+        rdzv.barrier()                                    # rank 1 keeps its memory mapped until rank 0 has given up
+        ens.close()
+        ref.close()
+        rdzv.close()
+        print("rank %d ok" % rank, flush=True)
+        return
     ens.run_mcmc(steps // 2, thin=thin)
     assert np.array_equal(ens.chains, ref.chains[:, 0]), "rank %d: chain differs from the one-GPU sampler" % rank
     assert np.array_equal(ens.lnprobs, ref.lnprobs[:, 0]), "rank %d: lnprob differs" % rank

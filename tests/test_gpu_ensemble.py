@@ -59,13 +59,12 @@ def test_single_rank_matches_persistent_sampler_and_large_ensemble():
             DeviceEnsembleSampler(mod2.compiled, 64, bad, seed=1)
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_ranks_reproduce_the_single_gpu_chain(world):
+def _run_ranks(world, *args):
     procs = []
     with tempfile.TemporaryDirectory() as rdzv:
         for r in range(world):
             env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), ISO_B200_RDZV=rdzv)
-            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_ensemble_worker.py")],
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_ensemble_worker.py")] + list(args),
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
         outs = []
         for p in procs:
@@ -76,5 +75,16 @@ def test_ranks_reproduce_the_single_gpu_chain(world):
                     q.kill()
                 raise
             outs.append((p.returncode, out))
-    for r, (rc, out) in enumerate(outs):
+    return outs
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_reproduce_the_single_gpu_chain(world):
+    for r, (rc, out) in enumerate(_run_ranks(world)):
         assert rc == 0 and ("rank %d ok" % r) in out, out[-3000:]
+
+
+def test_missing_rank_turns_into_a_timeout_error():
+    outs = _run_ranks(2, "timeout")
+    assert outs[0][0] == 0 and "rank 0 timeout reported" in outs[0][1], outs[0][1][-3000:]
+    assert outs[1][0] == 0, outs[1][1][-3000:]
