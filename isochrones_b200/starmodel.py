@@ -430,6 +430,8 @@ class BasicStarModel(object):
             sampler.reset()
         sampler.run_mcmc(niter, thin=thin)
         self._sampler = sampler
+        self._samples = self._derived_samples = None
+        self._sample_source = "mcmc"
         return sampler
 
     def fit_nested(self, n_live_points=1000, evidence_tolerance=0.5, seed=0, **kwargs):
@@ -440,7 +442,79 @@ class BasicStarModel(object):
         from .nested import nested_sample
 
         self._nested = nested_sample(self, n_live=n_live_points, dlogz=evidence_tolerance, seed=seed, **kwargs)
+        self._samples = self._derived_samples = None
+        self._sample_source = "nested"
         return self._nested
+
+    # ---- posterior samples and what follows from them ------------------------------------------
+    @property
+    def samples(self):
+        """Equal-weight posterior samples of the last fit as a DataFrame: the parameter columns + ``lnprob`` — what the
+        reference reads back from MultiNest's ``post_equal_weights.dat`` (starmodel.py:1652-1660).  After ``fit_nested``
+        the weighted points are resampled to equal weights; after ``fit_mcmc`` it is the flattened production chain."""
+        import pandas as pd
+
+        if self._samples is None:
+            source = getattr(self, "_sample_source", None)
+            if source == "nested":
+                res = self._nested
+                n = max(1, int(round(1.0 / np.sum(res.weights ** 2))))
+                pos = (np.random.default_rng(0).random() + np.arange(n)) / n
+                pick = np.minimum(np.searchsorted(np.cumsum(res.weights), pos), len(res.weights) - 1)
+                values, lnprob = res.samples[pick], res.lnpost[pick]
+            elif source == "mcmc":
+                values = self._sampler.chain.reshape(-1, self.n_params)
+                lnprob = self._sampler.lnprobability.reshape(-1)
+            else:
+                raise AttributeError("no samples yet: run fit_nested() or fit_mcmc() first")
+            df = pd.DataFrame(values, columns=list(self.param_names))
+            df["lnprob"] = lnprob
+            self._samples = df
+        return self._samples
+
+    @property
+    def derived_samples(self):
+        """The table ``derive(samples)`` of the last fit (starmodel.py:1646-1650)."""
+        if self._derived_samples is None:
+            self._derived_samples = self.derive(self.samples)
+        return self._derived_samples
+
+    def derive(self, samples):
+        """Posterior samples -> every model-grid column and every band's magnitude of every star, the reference's
+        derived-sample table (``_make_samples``, starmodel.py:1662-1714) — two batched launches per star (all-column
+        ``interp_values`` + ``interp_mags``) instead of a DataFrame round trip per call.
+
+        ``samples``: DataFrame with the ``param_names`` columns (others, e.g. ``lnprob``, are carried along for
+        multi-star models, as the reference does), or an ``[n, n_params]`` array.  Columns follow the reference: single
+        star = the interpolator's table (grid columns, ``<band>_mag``); N stars = the sample columns, then per star k
+        ``<column>_k`` / ``<band>_mag_k`` (without eep, age, distance, AV), then the combined ``<band>_mag``; always
+        ``parallax = 1000 / distance``, ``distance``, ``AV`` last."""
+        import pandas as pd
+
+        names = list(self.param_names)
+        if not isinstance(samples, pd.DataFrame):
+            samples = pd.DataFrame(np.atleast_2d(np.asarray(samples, dtype=np.float64)), columns=names)
+        col = {c: samples[c].to_numpy(dtype=np.float64) for c in names}
+        if self.N == 1:
+            table = self.ic(*[col[c] for c in names])
+        else:
+            shared = names[self.N:]                                 # age, feh, distance, AV
+            pieces = [samples.reset_index(drop=True)]
+            flux = {b: 0.0 for b in self.bands}
+            for k in range(self.N):
+                star = self.ic(col["eep_%d" % k], *[col[c] for c in shared])
+                for b in self.bands:                                # utils.py:43-58: fluxes add
+                    flux[b] = flux[b] + 10.0 ** (-0.4 * star[b + "_mag"].to_numpy())
+                star = star.drop(columns=["eep", "age"])
+                star.columns = ["%s_%d" % (c, k) for c in star.columns]
+                pieces.append(star)
+            table = pd.concat(pieces, axis=1)
+            for b in self.bands:
+                table[b + "_mag"] = -2.5 * np.log10(flux[b])
+        table["parallax"] = 1000.0 / col["distance"]
+        table["distance"] = col["distance"]
+        table["AV"] = col["AV"]
+        return table
 
     def sample_from_prior(self, n, values=False, require_valid=True):
         """Prior draws, re-drawn until ``lnpost`` is finite (starmodel.py:1716-1748); host RNG, batched validity check."""

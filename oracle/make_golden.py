@@ -410,13 +410,71 @@ def golden_eep(ref, out):
         else:
             out["mid_shape"] = np.array([7, 40, 342])
         print("eep", tag, "finite", int(np.isfinite(res).sum()), "nan", int(np.isnan(res).sum()))
+def golden_derived(ref, out):
+    """The reference's derived-sample table (``BasicStarModel.derived_samples``, starmodel.py:1646-1714): equal-weight
+    samples written where the reference expects MultiNest's ``post_equal_weights.dat``, read back and expanded by its own
+    ``_make_samples`` — single star on both grid kinds, a binary and a triple."""
+    import tempfile
+
+    trk, iso, bc = grids_small()
+    cases = {c[0]: c for c in model_cases()}
+    specs = {}
+    for name in ("track_full", "iso_single", "iso_binary", "iso_triple"):
+        _, kind, N, obs, init_kw, _ = cases[name]
+        model = trk if kind == "track" else iso
+        ic = ref_shim.make_ref_ic(kind, model, bc, eep_bounds=(0, 60))
+        truth = syn.default_truth(kind, n_eep=60, n_stars=N)
+        kwargs = dict(obs["spec"])
+        prim = [truth[0]] + list(truth[N:]) if kind == "iso" else list(truth)
+        _, _, _, mags = ic.interp_mag(prim, obs["bands"])
+        for i, b in enumerate(obs["bands"]):
+            kwargs[b] = (float(np.round(mags[i], 3) + 0.01 * (i - 1)), 0.02)
+        kwargs.update(obs["extra"])
+        mod = ref.starmodel.BasicStarModel(ic, N=N, **init_kw, **kwargs)
+        rows = syn.posterior_like_batch(kind, 48, truth, n_eep=60, seed=51)
+        rows[5, 0 if kind == "iso" else 1] = 1e4                      # one sample outside the grid: NaN row
+        lnprob = np.linspace(-30.0, -20.0, len(rows))
+        with tempfile.TemporaryDirectory() as d, warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod.mnest_basename = os.path.join(d, "fit-")
+            np.savetxt(mod.mnest_basename + "post_equal_weights.dat", np.column_stack([rows, lnprob]), fmt="%.17e")
+            # the installed pandas no longer knows read_csv(delim_whitespace=True) (starmodel.py:1656): same meaning, new
+            # spelling — a shim of the harness like the stubbed third-party modules, the reference file is untouched
+            import pandas as pd
+            real_read_csv = pd.read_csv
+
+            def read_csv(*a, **kw):
+                if kw.pop("delim_whitespace", False):
+                    kw["sep"] = r"\s+"
+                return real_read_csv(*a, **kw)
+            pd.read_csv = read_csv
+            try:
+                table = mod.derived_samples
+                sam = mod.samples
+            finally:
+                pd.read_csv = real_read_csv
+        # pandas' default float parser is not round-trip exact: the samples the reference actually expanded are the ones it
+        # read back
+        assert np.allclose(sam[list(mod.param_names)].values, rows, rtol=1e-14, atol=0)
+        rows = sam[list(mod.param_names)].values.astype(float)
+        lnprob = sam["lnprob"].values.astype(float)
+        out["dv_%s_rows" % name] = rows
+        out["dv_%s_lnprob" % name] = lnprob
+        out["dv_%s_values" % name] = table.values.astype(float)
+        specs[name] = {"kind": kind, "N": N, "kwargs": {k: [float(v[0]), float(v[1])] for k, v in kwargs.items()},
+                       "init_kwargs": init_kw, "columns": [str(c) for c in table.columns],
+                       "param_names": list(mod.param_names), "bands": list(mod.bands)}
+        print("%-12s %d columns, %d NaN cells" % (name, table.shape[1], int(np.isnan(table.values.astype(float)).sum())))
+    out["dv_specs_json"] = np.array(json.dumps(specs))
+
+
 def main():
     ref = ref_shim.load()
 
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("interp", golden_interp), ("mags", golden_mags), ("lnpost", golden_lnpost),
-                     ("priors", golden_priors), ("eep", golden_eep)):
+                     ("priors", golden_priors), ("eep", golden_eep), ("derived", golden_derived)):
         if only and name not in only:
             continue
         out = {}

@@ -111,6 +111,9 @@ class _FakeGrid:
         self._limits = dict(limits)
         self.eep_replaces = eep_replaces
         self.name = name
+        # ModelGridInterpolator.__call__ asks the grid's frame for its column names only (models.py:477)
+        import types
+        self.df = types.SimpleNamespace(columns=list(interp.columns))
 
     def get_limits(self, prop):
         return self._limits[prop]

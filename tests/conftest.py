@@ -18,4 +18,4 @@ def golden():
 
     d = os.path.join(ROOT, "tests", "golden")
     return {name: np.load(os.path.join(d, "golden_%s.npz" % name), allow_pickle=False)
-            for name in ("interp", "mags", "lnpost", "priors")}
+            for name in ("interp", "mags", "lnpost", "priors", "derived")}

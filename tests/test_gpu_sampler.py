@@ -147,3 +147,31 @@ def test_work_queue_of_multi_wave_runs_matches_the_oracle_chains(setup):
     assert (cnt == (n_steps // 8) * nw).all()
     assert np.allclose(mean, chain[7::8].mean(axis=(0, 2)), rtol=1e-11, atol=1e-11)
     smp.close()
+
+
+@pytest.mark.parametrize("kind", ["track", "iso"])
+def test_fit_mcmc_samples_and_derived_samples(setup, kind):
+    """`BasicStarModel.fit_mcmc` (burn-in, reset, production: starmodel.py:889-972) and what the reference builds from the
+    samples afterwards (`samples`, `derived_samples`: starmodel.py:1646-1714) — single star and binary."""
+    mod, _, truth, _ = setup[kind]
+    nw, niter = 64, 120
+    sampler = mod.fit_mcmc(nwalkers=nw, nburn=80, niter=niter, seed=5)
+    assert sampler.chain.shape == (nw, niter, mod.n_params) and sampler.lnprobability.shape == (nw, niter)
+    acc = float(np.mean(sampler.acceptance_fraction))
+    assert 0.05 < acc < 0.95, acc
+    sam = mod.samples
+    assert list(sam.columns) == list(mod.param_names) + ["lnprob"] and len(sam) == nw * niter
+    assert np.isfinite(sam["lnprob"]).all()
+    # lnprob IS the lnpost of the stored positions
+    again = mod.lnpost_batch(sam[list(mod.param_names)].to_numpy()[:500])
+    assert np.allclose(again, sam["lnprob"].to_numpy()[:500], rtol=1e-12, atol=1e-9)
+    der = mod.derived_samples
+    assert len(der) == len(sam) and list(der.columns)[-1] in ("AV", "parallax")
+    assert np.allclose(der["parallax"], 1000.0 / sam["distance"]) and np.array_equal(der["distance"], sam["distance"])
+    teff = "Teff" if mod.N == 1 else "Teff_0"
+    assert np.isfinite(der[teff]).all() and abs(np.median(der[teff]) - 5772.0) < 600.0
+    for b in mod.bands:
+        assert np.isfinite(der[b + "_mag"]).all()
+        if mod.N == 2:      # the system is brighter than either star
+            assert (der[b + "_mag"] < der[b + "_mag_0"]).all() and (der[b + "_mag"] < der[b + "_mag_1"]).all()
+    assert mod.derived_samples is der                     # cached until the next fit
