@@ -164,7 +164,7 @@ def _draw_from_union(ells, n, rng):
 
 
 def nested_sample(mod, n_live=1000, dlogz=0.5, seed=0, enlarge=1.25, batch=8192, max_iter=5_000_000, max_batches=20_000,
-                  return_dead=True, multi=True):
+                  return_dead=True, multi=True, max_init_draws=2_000_000_000):
     """Nested sampling of ``mod`` (a ``BasicStarModel``): returns a :class:`NestedResult`.
 
     ``n_live``: live points (MultiNest's ``n_live_points``, starmodel.py:667-671 default 1000); ``dlogz``: stop when the
@@ -200,8 +200,8 @@ def nested_sample(mod, n_live=1000, dlogz=0.5, seed=0, enlarge=1.25, batch=8192,
         live_u = np.concatenate([live_u, u[take]])
         live_p = np.concatenate([live_p, p[take]])
         live_l = np.concatenate([live_l, lp[take]])
-        if n_tried > 2_000_000_000:
-            raise RuntimeError("no finite lnpost in the prior box")
+        if n_tried > max_init_draws and len(live_l) < n_live:
+            raise RuntimeError("no finite lnpost in the prior box (%d of %d live points after %d draws)" % (len(live_l), n_live, n_tried))
     finite_fraction = n_live / float(n_tried)
     n_init = n_evals
 

@@ -79,3 +79,19 @@ def test_union_of_ellipsoids_is_sampled_uniformly():
     want = want if ells[0].mu[0] < 0.5 else 1.0 - want
     assert abs(share - want) < 0.02, (share, want)
     assert all(e.contains(pts[:300] if e.mu[0] < 0.5 else pts[300:]).all() for e in ells)
+
+
+def test_live_points_only_and_iteration_cap():
+    full = nested_sample(_Analytic(_two_gaussians, 3), n_live=400, seed=11)
+    lean = nested_sample(_Analytic(_two_gaussians, 3), n_live=400, seed=11, return_dead=False)
+    assert lean.logZ == full.logZ and lean.n_evals == full.n_evals          # same run, only the bookkeeping differs
+    assert lean.samples.shape == (400, 3) and abs(lean.weights.sum() - 1.0) < 1e-12
+    capped = nested_sample(_Analytic(_two_gaussians, 3), n_live=400, seed=11, max_iter=500)
+    assert not capped.converged and capped.n_iter == 500 and capped.logZ < full.logZ
+
+
+def test_everything_non_finite_raises():
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        nested_sample(_Analytic(lambda u: np.full(len(u), np.nan), 2), n_live=50, seed=0, max_init_draws=100_000)
