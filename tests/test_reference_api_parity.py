@@ -71,6 +71,8 @@ def test_star_models():
     assert _params(m.mnest_prior)[:1] == ["cube"] and _params(r.lnpost)[0] == _params(m.lnpost)[0] == "p"
     for prop in ("param_names", "bands", "props", "spec_props", "n_params", "labelstring", "ic"):
         assert isinstance(getattr(m, prop), property) and isinstance(getattr(r, prop), property), prop
+    for prop in ("samples", "derived_samples"):     # defined on the reference's StarModel base, inherited by BasicStarModel
+        assert isinstance(getattr(m, prop), property) and isinstance(getattr(r, prop), property), prop
     assert m._not_a_band == r._not_a_band
     for name in ("SingleStarModel", "BinaryStarModel", "TripleStarModel"):
         assert issubclass(getattr(S, name), S.BasicStarModel) and issubclass(getattr(ref.starmodel, name), r)
